@@ -1,0 +1,92 @@
+// common.cuh — shared host/device helpers for libyolov3_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/yolov3_b200.h"
+
+namespace y3 {
+
+// ---- host-side error plumbing (thread-local message, int status) ---------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define Y3_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      y3::set_error(__VA_ARGS__);               \
+      return Y3_EINVAL;                         \
+    }                                           \
+  } while (0)
+
+#define Y3_CUDA_OK(expr)                                                      \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      y3::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                    __FILE__, __LINE__);                                      \
+      return Y3_ECUDA;                                                        \
+    }                                                                         \
+  } while (0)
+
+// cudaGetLastError after a launch; counts the launch for y3_launch_count().
+#define Y3_LAUNCH_OK(name)                                                    \
+  do {                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                      \
+    if (e_ != cudaSuccess) {                                                  \
+      y3::set_error("launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+      return Y3_ECUDA;                                                        \
+    }                                                                         \
+    y3::count_launch();                                                       \
+  } while (0)
+
+int num_sms();  // SM count of the current device (cached per device)
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte streaming global accesses (activations are touched once per layer).
+__device__ __forceinline__ uint4 ld_nc_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_16(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+// max over packed bf16 pairs
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+__device__ __forceinline__ uint4 bf16x8_max(const uint4& a, const uint4& b) {
+  return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y),
+                    bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace y3

@@ -1,0 +1,473 @@
+// conv_umma.cu — Darknet [convolutional] block as an implicit GEMM on sm_100a.
+//
+// Replaces torch.nn.Conv2d + BatchNorm2d(eval) + LeakyReLU(0.1) as built at
+// yolov3/darknet.py:244-257 and executed at :367-368, with the shortcut add
+// (:376-379) and the nearest x2 upsample (:299-305) available as epilogue fusions.
+//
+//   D[M = N*Ho*Wo, Cout] = im2col(X)[M, K = R*S*Cin] * W[Cout, K]^T      (bf16 x bf16 -> fp32)
+//
+// Data path per CTA (persistent, one CTA per SM, 6 warps):
+//   warp 0  : TMA producer.  A tile = 128 output pixels x BLOCK_K channels of one filter tap,
+//             fetched by ONE im2col-mode TMA (zero-filled halo, stride handled by the tensor
+//             map) — or a plain 2-D tiled TMA for 1x1/s1.  B tile = BLOCK_N x BLOCK_K weights.
+//             Both land in 128B/64B/32B-swizzled K-major smem, STAGES-deep mbarrier ring.
+//   warp 1  : allocates TMEM; one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into one
+//             of two TMEM accumulator buffers; tcgen05.commit releases smem stages and
+//             publishes the finished accumulator.
+//   warps2-5: epilogue.  tcgen05.ld the accumulator (lane = output pixel), + folded-BN bias,
+//             LeakyReLU, + residual, convert, store NHWC (optionally to the 2x2 upsampled
+//             block, optionally into a channel slice of a concat buffer via ld_y).
+// The double-buffered accumulator lets tile i's epilogue overlap tile i+1's MMAs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cuda.h>  // CUtensorMap + enums only; entry points are fetched at run time
+
+namespace y3 {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 192;
+static constexpr int EPI_WARP0 = 2;  // first epilogue warp
+
+struct ConvKernelParams {
+  int M;           // output pixels N*Ho*Wo
+  int Ho, Wo, HoWo;
+  int cin_blocks;  // Cin / BLOCK_K
+  int num_kb;      // R*S*cin_blocks
+  int S;           // filter width
+  int stride, pad;
+  int num_m_tiles, num_n_tiles;
+  int a_tiled;     // 1: A via 2-D tiled map (1x1, stride 1); 0: im2col map
+  const float* bias;
+  void* out;
+  const __nv_bfloat16* res;
+  int ld_out, ld_res;
+  int leaky, out_f32, upsample;
+};
+
+template <int BLOCK_N, int BLOCK_K>
+struct ConvCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  // keep every stage 1024B-aligned (required for SWIZZLE_128B, harmless otherwise)
+  static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_STRIDE + B_STRIDE;
+  static constexpr int STAGES_RAW = 196608 / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int TMEM_COLS_RAW = 2 * BLOCK_N;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
+                                 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // UMMA smem descriptor pieces (K-major, swizzle span = BLOCK_K*2 bytes)
+  static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
+  static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
+  static constexpr uint64_t DESC_HI = ((SBO >> 4) << 32) | (1ull << 46) | (LAYOUT_TYPE << 61);
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) |
+                                    (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t desc_hi) {
+  return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
+}
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const int img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int ho0 = rem / p.Wo;
+        const int wo0 = rem - ho0 * p.Wo;
+        const int w_base = wo0 * p.stride - p.pad;
+        const int h_base = ho0 * p.stride - p.pad;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_STRIDE;
+          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+          if (p.a_tiled) {
+            ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), cb * BLOCK_K, m0);
+          } else {
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            ptx::tma_load_im2col_4d(a_dst, &tmap_a, full_bar(stage), cb * BLOCK_K, w_base, h_base,
+                                    img, (uint16_t)s, (uint16_t)r);
+          }
+          ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this buffer
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_STRIDE;
+          const uint64_t desc_a = make_smem_desc(a_addr, Cfg::DESC_HI);
+          const uint64_t desc_b = make_smem_desc(b_addr, Cfg::DESC_HI);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the swizzle span: +2 in the >>4 address field
+            ptx::umma_bf16_ss(tmem_d, desc_a + 2u * k, desc_b + 2u * k, Cfg::IDESC,
+                              (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(tfull_bar(acc));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const int row = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m = m_tile * BLOCK_M + row;
+      const int n0 = n_tile * BLOCK_N;
+      const bool valid = m < p.M;
+
+      // destination pixel index(es)
+      long long dst_pix = m;
+      int up_w2 = 0;
+      if (p.upsample) {
+        const int img = m / p.HoWo;
+        const int rem = m - img * p.HoWo;
+        const int ho = rem / p.Wo;
+        const int wo = rem - ho * p.Wo;
+        up_w2 = 2 * p.Wo;
+        dst_pix = ((long long)img * (2 * p.Ho) + 2 * ho) * up_w2 + 2 * wo;
+      }
+      const __nv_bfloat16* res_row = p.res ? p.res + (long long)m * p.ld_res + n0 : nullptr;
+
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_x16(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        float f[16];
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = __ldg(bias4 + q);
+          f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+          f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+          f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+        }
+        if (p.leaky) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+        }
+        if (valid) {
+          if (res_row) {
+            const uint4 r0 = ld_nc_16(res_row + c0);
+            const uint4 r1 = ld_nc_16(res_row + c0 + 8);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 t = unpack_bf16x2(rr[j]);
+              f[2 * j] += t.x;
+              f[2 * j + 1] += t.y;
+            }
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + dst_pix * p.ld_out + n0 + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_16(o + 4 * q, make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                          __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
+          } else {
+            const uint4 o0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            const uint4 o1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                        pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dst_pix * p.ld_out + n0 + c0;
+            st_16(o, o0);
+            st_16(o + 8, o1);
+            if (p.upsample) {
+              __nv_bfloat16* o01 = o + p.ld_out;
+              __nv_bfloat16* o10 = o + (long long)up_w2 * p.ld_out;
+              __nv_bfloat16* o11 = o10 + p.ld_out;
+              st_16(o01, o0); st_16(o01 + 8, o1);
+              st_16(o10, o0); st_16(o10 + 8, o1);
+              st_16(o11, o0); st_16(o11 + 8, o1);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side: tensor-map encoding (driver entry points resolved through the runtime so the
+// library has no link-time dependency on libcuda and loads on a CPU-only box).
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int resolve_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return Y3_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  Y3_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return Y3_ECUDA;
+  }
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  Y3_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeIm2col not available from the driver");
+    return Y3_ECUDA;
+  }
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  Y3_CUDA_OK(cudaDriverGetVersion(&g_driver_version));
+  return Y3_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for(int block_k) {
+  return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+       : block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer, int block_k) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): dims=[%llu,%llu] pitch=%llu box=[%u,%u]",
+              (int)r, (unsigned long long)inner, (unsigned long long)outer,
+              (unsigned long long)pitch_bytes, box_inner, box_outer);
+    return Y3_ECUDA;
+  }
+  return Y3_OK;
+}
+
+static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x, int block_k) {
+  cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+  const uint64_t pix = (uint64_t)d->ld_x * 2;
+  cuuint64_t strides[3] = {pix, pix * d->w, pix * d->w * d->h};
+  // Bounding box of filter-window origins in input coordinates:
+  // from -pad to (extent-1) + pad - (ksize-1)  (see SURVEY.md §7 step 3).
+  int lower[2] = {-d->pad, -d->pad};
+  int upper[2] = {d->pad - (d->ksize - 1), d->pad - (d->ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims,
+                               strides, lower, upper, (cuuint32_t)block_k, (cuuint32_t)BLOCK_M, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (CUresult %d): dims=[%d,%d,%d,%d] ld=%d k=%d s=%d p=%d",
+              (int)r, d->cin, d->w, d->h, d->n, d->ld_x, d->ksize, d->stride, d->pad);
+    return Y3_ECUDA;
+  }
+  // Drivers up to CUDA 13.1 mis-encode im2col maps of tensors smaller than 128 KiB
+  // (descriptor word 1, bit 21 must be clear); same fix-up NVIDIA's own templates apply.
+  if (g_driver_version <= 13010) {
+    const uint64_t extent = pix * d->w * d->h * (uint64_t)d->n;
+    if (extent < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  }
+  return Y3_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                       const void* residual, void* y, cudaStream_t stream, int force_im2col) {
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K>;
+  const int ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
+  const int wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
+  const long long M = (long long)d->n * ho * wo;
+  Y3_CHECK_ARG(M > 0 && M < (1ll << 31) - BLOCK_M, "conv: M=%lld out of range", M);
+
+  ConvKernelParams p;
+  p.M = (int)M;
+  p.Ho = ho; p.Wo = wo; p.HoWo = ho * wo;
+  p.cin_blocks = d->cin / BLOCK_K;
+  p.num_kb = d->ksize * d->ksize * p.cin_blocks;
+  p.S = d->ksize;
+  p.stride = d->stride; p.pad = d->pad;
+  p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_tiles = d->cout / BLOCK_N;
+  p.a_tiled = (d->ksize == 1 && d->stride == 1 && d->pad == 0 && !force_im2col) ? 1 : 0;
+  p.bias = bias;
+  p.out = y;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.ld_out = d->ld_y; p.ld_res = d->ld_res;
+  p.leaky = d->leaky; p.out_f32 = d->out_f32; p.upsample = d->upsample2x;
+
+  int rc = resolve_driver_entry_points();
+  if (rc != Y3_OK) return rc;
+
+  alignas(64) CUtensorMap tmap_a, tmap_b;
+  if (p.a_tiled) {
+    rc = encode_2d(&tmap_a, x, (uint64_t)d->cin, (uint64_t)d->n * d->h * d->w, (uint64_t)d->ld_x * 2,
+                   BLOCK_K, BLOCK_M, BLOCK_K);
+  } else {
+    rc = encode_im2col(&tmap_a, d, x, BLOCK_K);
+  }
+  if (rc != Y3_OK) return rc;
+  const uint64_t k_total = (uint64_t)d->ksize * d->ksize * d->cin;
+  rc = encode_2d(&tmap_b, w, k_total, (uint64_t)d->cout, k_total * 2, BLOCK_K, BLOCK_N, BLOCK_K);
+  if (rc != Y3_OK) return rc;
+
+  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    Y3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kernel<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmap_a, tmap_b, p);
+  Y3_LAUNCH_OK("conv_umma_kernel");
+  return Y3_OK;
+}
+
+template <int BLOCK_K>
+static int dispatch_n(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                      const void* residual, void* y, cudaStream_t stream, int force_im2col) {
+  const int c = d->cout;
+  if (c % 256 == 0) return launch_conv<256, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 128 == 0) return launch_conv<128, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 64 == 0) return launch_conv<64, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 32 == 0) return launch_conv<32, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  return launch_conv<16, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+}
+
+static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                       const void* residual, void* y, void* stream, int force_im2col) {
+  Y3_CHECK_ARG(d && x && w && bias && y, "conv: null argument");
+  Y3_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "conv: bad input shape %dx%dx%d", d->n, d->h, d->w);
+  Y3_CHECK_ARG(d->cin > 0 && d->cin % 16 == 0, "conv: cin=%d must be a positive multiple of 16", d->cin);
+  Y3_CHECK_ARG(d->cout > 0 && d->cout % 16 == 0, "conv: cout=%d must be a positive multiple of 16", d->cout);
+  Y3_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv: ksize=%d unsupported (1 or 3)", d->ksize);
+  Y3_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv: stride=%d unsupported (1 or 2)", d->stride);
+  Y3_CHECK_ARG(d->pad == 0 || d->pad == (d->ksize - 1) / 2, "conv: pad=%d unsupported", d->pad);
+  Y3_CHECK_ARG(d->h + 2 * d->pad >= d->ksize && d->w + 2 * d->pad >= d->ksize, "conv: input smaller than filter");
+  Y3_CHECK_ARG(d->ld_x >= d->cin && d->ld_x % 8 == 0, "conv: ld_x=%d must be >= cin and a multiple of 8", d->ld_x);
+  Y3_CHECK_ARG(d->ld_y >= d->cout && d->ld_y % (d->out_f32 ? 4 : 8) == 0, "conv: ld_y=%d invalid", d->ld_y);
+  Y3_CHECK_ARG(!residual || (d->ld_res >= d->cout && d->ld_res % 8 == 0), "conv: ld_res=%d invalid", d->ld_res);
+  Y3_CHECK_ARG(!(d->upsample2x && d->out_f32), "conv: upsample2x with out_f32 unsupported");
+  Y3_CHECK_ARG(!(d->upsample2x && residual), "conv: upsample2x with residual unsupported");
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+               "conv: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->cin % 64 == 0) return dispatch_n<64>(d, x, w, bias, residual, y, s, force_im2col);
+  if (d->cin % 32 == 0) return dispatch_n<32>(d, x, w, bias, residual, y, s, force_im2col);
+  return dispatch_n<16>(d, x, w, bias, residual, y, s, force_im2col);
+}
+
+}  // namespace y3
+
+extern "C" int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                         const void* residual, void* y, void* stream) {
+  return y3::conv2d_impl(d, x, w, bias, residual, y, stream, d ? (d->flags & 1) : 0);
+}

@@ -1,0 +1,189 @@
+// decode.cu — YOLO head decode (yolov3/darknet.py:48-122, :390-399) and the per-image
+// post-processing of yolov3/inference.py:342-353 + cxywh_to_tlbr (:269-283), fused.
+//
+// One warp decodes one box (image, anchor, row, col): its 5+classes logits are contiguous in
+// the NHWC float32 head tensor, so the warp reads them with coalesced 128-byte requests, finds
+// max/argmax and the softmax denominator with shuffles, and lane 0 finishes the box.
+// All fp32 steps keep the reference's operation order (sigmoid, +offset, /grid; exp, *anchor,
+// /train size, *image size) with explicit round-to-nearest intrinsics so no FMA contraction
+// changes a rounding; only sigmoid/exp themselves may differ from torch's by an ulp.
+#include "common.cuh"
+
+namespace y3 {
+
+struct BoxOut {
+  float x, y, w, h, prob;
+  int cls;
+};
+
+__device__ __forceinline__ float sigmoidf_ref(float v) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+}
+
+// Whole warp cooperates; result valid in every lane.
+__device__ __forceinline__ BoxOut decode_box(const y3_head_desc& d, const float* __restrict__ logits,
+                                             int img, int a, int row, int col, int lane) {
+  const int fields = 5 + d.num_classes;
+  const float* px = logits + ((long long)(img * d.g_h + row) * d.g_w + col) * d.ld + a * fields;
+  // lanes 0..4 hold tx,ty,tw,th,to from the first request
+  float head = (lane < fields) ? __ldg(px + lane) : 0.f;
+  float best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  for (int f = lane; f < fields; f += 32) {
+    const float v = (f == lane) ? head : __ldg(px + f);
+    if (f >= 5 && (v > best)) { best = v; best_idx = f - 5; }
+  }
+  // warp arg-max (first index wins ties, like torch.max)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+  }
+  float sum = 0.f;
+  for (int f = lane; f < fields; f += 32) {
+    if (f >= 5) {
+      const float v = (f == lane) ? head : __ldg(px + f);
+      sum += expf(v - best);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+
+  const float tx = __shfl_sync(0xffffffffu, head, 0);
+  const float ty = __shfl_sync(0xffffffffu, head, 1);
+  const float tw = __shfl_sync(0xffffffffu, head, 2);
+  const float th = __shfl_sync(0xffffffffu, head, 3);
+  const float to = __shfl_sync(0xffffffffu, head, 4);
+
+  BoxOut o;
+  o.x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)d.g_w);
+  o.y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)d.g_h);
+  o.w = __fdiv_rn(__fmul_rn(expf(tw), d.anchor_w[a]), d.train_w);
+  o.h = __fdiv_rn(__fmul_rn(expf(th), d.anchor_h[a]), d.train_h);
+  // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)
+  o.prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
+  o.cls = best_idx;
+  return o;
+}
+
+__device__ __forceinline__ bool next_box(const y3_head_desc& d, long long wid, int& img, int& a,
+                                         int& row, int& col, int& m) {
+  const int cells = d.g_h * d.g_w;
+  const long long per_img = (long long)d.num_anchors * cells;
+  if (wid >= per_img * d.n) return false;
+  img = (int)(wid / per_img);
+  m = (int)(wid - (long long)img * per_img);  // a*cells + row*g_w + col  (darknet.py:118-120)
+  a = m / cells;
+  const int cell = m - a * cells;
+  row = cell / d.g_w;
+  col = cell - row * d.g_w;
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, float* __restrict__ bbox,
+                    float* __restrict__ prob, long long* __restrict__ cls) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;; wid += warps) {
+    int img, a, row, col, m;
+    if (!next_box(d, wid, img, a, row, col, m)) break;
+    const BoxOut o = decode_box(d, logits, img, a, row, col, lane);
+    if (lane == 0) {
+      const long long g = (long long)img * d.boxes_per_image + d.box_offset + m;
+      reinterpret_cast<float4*>(bbox)[g] = make_float4(o.x, o.y, o.w, o.h);
+      prob[g] = o.prob;
+      cls[g] = (long long)o.cls;
+    }
+  }
+}
+
+__device__ __forceinline__ int f2i_trunc(float v) {
+  // numpy astype(int) truncates toward zero; values stay far inside int32 for any sane logit
+  return __float2int_rz(v);
+}
+
+__global__ void __launch_bounds__(256)
+decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
+                    const int* __restrict__ orig_hw, y3_cand* __restrict__ cands,
+                    int* __restrict__ counts, int cap) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;; wid += warps) {
+    int img, a, row, col, m;
+    if (!next_box(d, wid, img, a, row, col, m)) break;
+    const BoxOut o = decode_box(d, logits, img, a, row, col, lane);
+    if (lane == 0 && o.prob >= prob_thresh) {  // inference.py:342
+      const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
+      const int cx = f2i_trunc(__fmul_rn(o.x, ow));  // inference.py:351-353
+      const int cy = f2i_trunc(__fmul_rn(o.y, oh));
+      const int bw = f2i_trunc(__fmul_rn(o.w, ow));
+      const int bh = f2i_trunc(__fmul_rn(o.h, oh));
+      // cxywh_to_tlbr: c -/+ wh // 2 (floor division; wh >= 0)
+      const int hw = bw >> 1, hh = bh >> 1;
+      const int slot = atomicAdd(counts + img, 1);
+      if (slot < cap) {
+        y3_cand c;
+        c.x1 = cx - hw; c.y1 = cy - hh; c.x2 = cx + hw; c.y2 = cy + hh;
+        c.prob = o.prob; c.cls = o.cls; c.box = d.box_offset + m; c.pad_ = 0;
+        reinterpret_cast<uint4*>(cands + (long long)img * cap + slot)[0] =
+            make_uint4((uint32_t)c.x1, (uint32_t)c.y1, (uint32_t)c.x2, (uint32_t)c.y2);
+        reinterpret_cast<uint4*>(cands + (long long)img * cap + slot)[1] =
+            make_uint4(__float_as_uint(c.prob), (uint32_t)c.cls, (uint32_t)c.box, 0u);
+      }
+    }
+  }
+}
+
+static int check_head(const y3_head_desc* d, const float* logits) {
+  Y3_CHECK_ARG(d && logits, "decode: null argument");
+  Y3_CHECK_ARG(d->n > 0 && d->g_h > 0 && d->g_w > 0, "decode: bad grid");
+  Y3_CHECK_ARG(d->num_anchors > 0 && d->num_anchors <= 8, "decode: num_anchors=%d out of range", d->num_anchors);
+  Y3_CHECK_ARG(d->num_classes > 0 && d->num_classes <= 1024, "decode: num_classes=%d out of range", d->num_classes);
+  Y3_CHECK_ARG(d->ld >= d->num_anchors * (5 + d->num_classes), "decode: ld=%d too small", d->ld);
+  Y3_CHECK_ARG(d->box_offset >= 0 && d->boxes_per_image >= d->box_offset + d->num_anchors * d->g_h * d->g_w,
+               "decode: box_offset/boxes_per_image inconsistent");
+  Y3_CHECK_ARG(d->train_w > 0 && d->train_h > 0, "decode: bad train size");
+  return Y3_OK;
+}
+
+static int decode_grid(const y3_head_desc* d) {
+  const long long boxes = (long long)d->n * d->num_anchors * d->g_h * d->g_w;
+  long long blocks = (boxes + 7) / 8;  // 8 warps per 256-thread CTA
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace y3
+
+using namespace y3;
+
+extern "C" {
+
+int y3_yolo_decode_dense(const y3_head_desc* d, const float* logits, float* bbox_xywh, float* class_prob,
+                         int64_t* class_idx, void* stream) {
+  int rc = check_head(d, logits);
+  if (rc != Y3_OK) return rc;
+  Y3_CHECK_ARG(bbox_xywh && class_prob && class_idx, "decode_dense: null output");
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(bbox_xywh) & 15) == 0, "decode_dense: bbox must be 16-byte aligned");
+  decode_dense_kernel<<<decode_grid(d), 256, 0, (cudaStream_t)stream>>>(
+      *d, logits, bbox_xywh, class_prob, reinterpret_cast<long long*>(class_idx));
+  Y3_LAUNCH_OK("decode_dense_kernel");
+  return Y3_OK;
+}
+
+int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits, float prob_thresh, const int32_t* orig_hw,
+                         y3_cand* cands, int32_t* counts, int32_t cap, void* stream) {
+  int rc = check_head(d, logits);
+  if (rc != Y3_OK) return rc;
+  Y3_CHECK_ARG(orig_hw && cands && counts && cap > 0, "decode_cands: bad output arguments");
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0, "decode_cands: cands must be 16-byte aligned");
+  decode_cands_kernel<<<decode_grid(d), 256, 0, (cudaStream_t)stream>>>(*d, logits, prob_thresh, orig_hw, cands,
+                                                                         counts, cap);
+  Y3_LAUNCH_OK("decode_cands_kernel");
+  return Y3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// nms.cu — greedy IoU suppression, bit-exact with the reference's NumPy implementation
+// (_non_max_suppression, yolov3/inference.py:161-217; per-class driver, :220-266).
+//
+// Three kernels, all integer / fp64-compare work on a few hundred KB per image:
+//   1. nms_bucket_kernel   one CTA per image: class histogram in shared memory, exclusive
+//                          scan, scatter of the candidates into per-class segments.
+//   2. nms_segment_kernel  one CTA per (image, class) segment: rank-sort the segment by
+//                          (prob desc, box asc), then greedy suppression in chunks of 32
+//                          pivots — warp 0 builds the 32x32 IoU bitmask of a chunk with
+//                          shuffles and resolves it with ballots, then every thread tests its
+//                          later boxes against the chunk's KEPT pivots only.
+//   3. nms_compact_kernel  ordered compaction of the kept records (block scan).
+// IoU follows the reference exactly: "+1" pixel areas in int64, iou = inter/union as an IEEE
+// float64 divide, suppressed iff iou > thresh.
+#include "common.cuh"
+
+namespace y3 {
+
+static constexpr int MAX_CLASSES = 1024;
+
+struct Box4 { int x1, y1, x2, y2; };
+
+__device__ __forceinline__ bool iou_gt(const Box4& a, const Box4& b, double thr) {
+  const long long area_a = ((long long)a.x2 - a.x1 + 1) * ((long long)a.y2 - a.y1 + 1);
+  const long long area_b = ((long long)b.x2 - b.x1 + 1) * ((long long)b.y2 - b.y1 + 1);
+  long long iw = (long long)min(a.x2, b.x2) - (long long)max(a.x1, b.x1) + 1;
+  long long ih = (long long)min(a.y2, b.y2) - (long long)max(a.y1, b.y1) + 1;
+  iw = iw > 0 ? iw : 0;
+  ih = ih > 0 ? ih : 0;
+  const long long inter = iw * ih;
+  const long long uni = area_a + area_b - inter;
+  const double iou = __ddiv_rn((double)inter, (double)uni);
+  return iou > thr;
+}
+
+// workspace layout (int32 words): seg_off [N][C+1] | cursor [N][C]
+// class-agnostic mode uses C = 1.
+
+__global__ void __launch_bounds__(1024)
+nms_bucket_kernel(const y3_cand* __restrict__ cands, const int* __restrict__ counts, int cap,
+                  int num_classes, int per_class, y3_cand* __restrict__ bucketed,
+                  int* __restrict__ seg_off, int* __restrict__ class_first_box) {
+  __shared__ int hist[MAX_CLASSES];
+  __shared__ int first[MAX_CLASSES];
+  __shared__ int offs[MAX_CLASSES + 1];
+  const int img = blockIdx.x;
+  const int C = per_class ? num_classes : 1;
+  int n = counts[img];
+  n = n < cap ? n : cap;
+  const y3_cand* src = cands + (long long)img * cap;
+  y3_cand* dst = bucketed + (long long)img * cap;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { hist[c] = 0; first[c] = 0x7fffffff; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int c = per_class ? src[i].cls : 0;
+    c = min(max(c, 0), C - 1);
+    atomicAdd(&hist[c], 1);
+    atomicMin(&first[c], src[i].box);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // C <= 1024: a serial scan is a few hundred cycles
+    int run = 0;
+    for (int c = 0; c < C; ++c) { offs[c] = run; run += hist[c]; }
+    offs[C] = run;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) seg_off[(long long)img * (C + 1) + c] = offs[c];
+  if (class_first_box)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) class_first_box[(long long)img * C + c] = first[c];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) hist[c] = 0;  // reuse as cursors
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+    const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+    int c = per_class ? (int)hi.y : 0;
+    c = min(max(c, 0), C - 1);
+    const int pos = offs[c] + atomicAdd(&hist[c], 1);
+    reinterpret_cast<uint4*>(dst + pos)[0] = lo;
+    reinterpret_cast<uint4*>(dst + pos)[1] = hi;
+  }
+}
+
+// key order: higher prob first; ties by lower box index (the reference's tie order is
+// unspecified — np.argsort is not stable — so any deterministic rule is admissible).
+__device__ __forceinline__ bool before(float pa, int ba, float pb, int bb) {
+  return pa > pb || (pa == pb && ba < bb);
+}
+
+__global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
+                                   int cap, int C, double thr, y3_cand* __restrict__ sorted,
+                                   uint8_t* __restrict__ keep) {
+  extern __shared__ uint8_t alive[];  // one byte per box of the segment
+  __shared__ uint32_t kept_mask_s;
+  const int img = blockIdx.y;
+  const int seg = blockIdx.x;
+  const int off = seg_off[(long long)img * (C + 1) + seg];
+  const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
+  if (n <= 0) return;
+  const y3_cand* src = bucketed + (long long)img * cap + off;
+  y3_cand* out = sorted + (long long)img * cap + off;
+  uint8_t* keep_out = keep + (long long)img * cap + off;
+
+  // ---- rank sort --------------------------------------------------------------------
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+    const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+    const float p = __uint_as_float(hi.x);
+    const int b = (int)hi.z;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const uint4 hj = reinterpret_cast<const uint4*>(src + j)[1];
+      rank += before(__uint_as_float(hj.x), (int)hj.z, p, b) ? 1 : 0;
+    }
+    reinterpret_cast<uint4*>(out + rank)[0] = lo;
+    reinterpret_cast<uint4*>(out + rank)[1] = hi;
+    alive[i] = 1;
+  }
+  __syncthreads();  // global writes to `out` by this CTA are visible to it from here on
+
+  // ---- greedy suppression, 32 pivots at a time ------------------------------------------
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    if (warp == 0) {
+      const int j = c0 + lane;
+      const bool valid = j < n;
+      Box4 mine = {0, 0, 0, 0};
+      if (valid) {
+        const int4 v = reinterpret_cast<const int4*>(out + j)[0];
+        mine = {v.x, v.y, v.z, v.w};
+      }
+      const bool was_alive = valid && alive[valid ? j : 0];
+      // bit i of sup: pivot i (earlier in order) would suppress me
+      uint32_t sup = 0;
+      for (int i = 0; i < 32; ++i) {
+        Box4 pi;
+        pi.x1 = __shfl_sync(0xffffffffu, mine.x1, i);
+        pi.y1 = __shfl_sync(0xffffffffu, mine.y1, i);
+        pi.x2 = __shfl_sync(0xffffffffu, mine.x2, i);
+        pi.y2 = __shfl_sync(0xffffffffu, mine.y2, i);
+        if (i < lane && valid && iou_gt(pi, mine, thr)) sup |= 1u << i;
+      }
+      uint32_t kept = 0;
+      for (int i = 0; i < 32; ++i) {
+        const bool k = (lane == i) && was_alive && ((sup & kept) == 0);
+        kept |= __ballot_sync(0xffffffffu, k);
+      }
+      if (valid) {
+        const uint8_t k = (kept >> lane) & 1u;
+        alive[j] = k;
+        keep_out[j] = k;
+      }
+      if (lane == 0) kept_mask_s = kept;
+    }
+    __syncthreads();
+    const uint32_t kept = kept_mask_s;
+    if (kept != 0) {
+      for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
+        if (!alive[j]) continue;
+        const int4 v = reinterpret_cast<const int4*>(out + j)[0];
+        const Box4 mine = {v.x, v.y, v.z, v.w};
+        uint32_t m = kept;
+        while (m) {
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          const int4 pv = reinterpret_cast<const int4*>(out + c0 + i)[0];
+          const Box4 pivot = {pv.x, pv.y, pv.z, pv.w};
+          if (iou_gt(pivot, mine, thr)) { alive[j] = 0; break; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Ordered compaction of kept records per image; dets are written image after image into one
+// flat array, det_offsets[img] .. det_offsets[img+1] (exclusive scan done by nms_offsets_kernel).
+__global__ void __launch_bounds__(1024)
+nms_count_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ counts, int cap,
+                 int* __restrict__ det_counts) {
+  __shared__ int total;
+  const int img = blockIdx.x;
+  int n = counts[img];
+  n = n < cap ? n : cap;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) local += keep[(long long)img * cap + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) det_counts[img] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+nms_compact_kernel(const y3_cand* __restrict__ sorted, const uint8_t* __restrict__ keep,
+                   const int* __restrict__ counts, int cap, y3_cand* __restrict__ dets,
+                   const int* __restrict__ det_counts, int n_images, int flat) {
+  __shared__ int warp_sums[32];
+  __shared__ int base_s;
+  const int img = blockIdx.x;
+  int n = counts[img];
+  n = n < cap ? n : cap;
+  // destination base: flat -> exclusive sum of det_counts of earlier images; else img*cap
+  if (threadIdx.x == 0) {
+    long long b = 0;
+    if (flat) { for (int i = 0; i < img; ++i) b += det_counts[i]; }
+    else b = (long long)img * cap;
+    base_s = (int)b;
+  }
+  __syncthreads();
+  int running = base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const int k = (i < n) ? keep[(long long)img * cap + i] : 0;
+    const uint32_t ball = __ballot_sync(0xffffffffu, k);
+    const int prefix = __popc(ball & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[warp] = __popc(ball);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) { const int s = warp_sums[w]; if (w < warp) woff += s; tot += s; }
+    if (k) {
+      const y3_cand* s = sorted + (long long)img * cap + i;
+      y3_cand* d = dets + running + woff + prefix;
+      reinterpret_cast<uint4*>(d)[0] = reinterpret_cast<const uint4*>(s)[0];
+      reinterpret_cast<uint4*>(d)[1] = reinterpret_cast<const uint4*>(s)[1];
+    }
+    running += tot;
+    __syncthreads();
+  }
+}
+
+}  // namespace y3
+
+using namespace y3;
+
+extern "C" {
+
+size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes) {
+  if (n <= 0 || cap <= 0 || num_classes <= 0) return 0;
+  const size_t bucketed = (size_t)n * cap * sizeof(y3_cand);
+  const size_t seg = (size_t)n * ((size_t)num_classes + 1) * sizeof(int32_t);
+  return bucketed + ((seg + 255) / 256) * 256 + 256;
+}
+
+int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, int32_t num_classes,
+           double iou_thresh, int32_t per_class, y3_cand* sorted, uint8_t* keep, int32_t* class_first_box,
+           void* workspace, size_t workspace_bytes, void* stream) {
+  Y3_CHECK_ARG(cands && counts && sorted && keep && workspace, "nms: null argument");
+  Y3_CHECK_ARG(n > 0 && cap > 0, "nms: bad n=%d cap=%d", n, cap);
+  Y3_CHECK_ARG(num_classes > 0 && num_classes <= MAX_CLASSES, "nms: num_classes=%d out of range (1..%d)",
+               num_classes, MAX_CLASSES);
+  Y3_CHECK_ARG(cap <= 200 * 1024, "nms: cap=%d exceeds the shared-memory flag array (204800)", cap);
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0 && (reinterpret_cast<uintptr_t>(sorted) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "nms: buffers must be 16-byte aligned");
+  if (workspace_bytes < y3_nms_workspace_bytes(n, cap, num_classes)) {
+    y3::set_error("nms: workspace %zu bytes < required %zu", workspace_bytes,
+                  y3_nms_workspace_bytes(n, cap, num_classes));
+    return Y3_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int C = per_class ? num_classes : 1;
+  y3_cand* bucketed = reinterpret_cast<y3_cand*>(workspace);
+  int* seg_off = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)n * cap * sizeof(y3_cand));
+
+  nms_bucket_kernel<<<n, 1024, 0, s>>>(cands, counts, cap, num_classes, per_class, bucketed, seg_off,
+                                       class_first_box);
+  Y3_LAUNCH_OK("nms_bucket_kernel");
+
+  // alive[] needs one byte per box of the largest possible segment (= cap)
+  const size_t smem = ((size_t)cap + 15) / 16 * 16;
+  static size_t smem_attr = 0;
+  if (smem > 48 * 1024 && smem > smem_attr) {
+    Y3_CUDA_OK(cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  const int threads = per_class ? 128 : 1024;
+  nms_segment_kernel<<<dim3(C, n), threads, smem, s>>>(bucketed, seg_off, cap, C, iou_thresh, sorted, keep);
+  Y3_LAUNCH_OK("nms_segment_kernel");
+  return Y3_OK;
+}
+
+int y3_compact_kept(const y3_cand* sorted, const uint8_t* keep, const int32_t* counts, int32_t n, int32_t cap,
+                    y3_cand* dets, int32_t* det_counts, int32_t flat, void* stream) {
+  Y3_CHECK_ARG(sorted && keep && counts && dets && det_counts, "compact_kept: null argument");
+  Y3_CHECK_ARG(n > 0 && cap > 0, "compact_kept: bad n=%d cap=%d", n, cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  nms_count_kernel<<<n, 1024, 0, s>>>(keep, counts, cap, det_counts);
+  Y3_LAUNCH_OK("nms_count_kernel");
+  nms_compact_kernel<<<n, 1024, 0, s>>>(sorted, keep, counts, cap, dets, det_counts, n, flat);
+  Y3_LAUNCH_OK("nms_compact_kernel");
+  return Y3_OK;
+}
+
+}  // extern "C"

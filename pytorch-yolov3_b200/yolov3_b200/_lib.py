@@ -1,0 +1,208 @@
+"""ctypes binding of ``libyolov3_b200.so`` (C ABI declared in ``include/yolov3_b200.h``).
+
+PyTorch is used for device memory and streams only: every wrapper takes torch
+tensors, passes ``data_ptr()`` / shapes / the current CUDA stream through the
+C ABI, and raises ``RuntimeError`` with ``y3_last_error()`` on a non-zero status.
+There is no fallback: if the shared library is missing this module raises at
+import of the first symbol (``lib()``), and every kernel wrapper refuses CPU
+tensors.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
+
+# Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
+EXPORTS = (
+    "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
+    "y3_conv2d", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
+    "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
+    "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept",
+)
+
+ABI_VERSION = 1
+
+
+class ConvDesc(ctypes.Structure):
+    """``y3_conv_desc``."""
+    _fields_ = [(n, c_int32) for n in (
+        "n", "h", "w", "cin", "cout", "ksize", "stride", "pad", "ld_x", "ld_y", "ld_res",
+        "leaky", "out_f32", "upsample2x", "flags")]
+
+
+class HeadDesc(ctypes.Structure):
+    """``y3_head_desc``."""
+    _fields_ = [(n, c_int32) for n in (
+        "n", "g_h", "g_w", "num_anchors", "num_classes", "ld", "box_offset", "boxes_per_image")] + [
+        ("anchor_w", c_float * 8), ("anchor_h", c_float * 8), ("train_w", c_float), ("train_h", c_float)]
+
+
+# numpy / torch view of ``y3_cand`` (32 bytes)
+CAND_WORDS = 8  # int32 words per record: x1 y1 x2 y2 prob(f32 bits) cls box pad
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C pytorch-yolov3_b200/csrc`). yolov3_b200 has no CPU / eager fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.y3_abi_version.restype = ctypes.c_int
+    L.y3_last_error.restype = c_char_p
+    L.y3_check_device.argtypes = [ctypes.c_int]
+    L.y3_launch_count.restype = c_longlong
+    L.y3_reset_launch_count.restype = None
+    L.y3_conv2d.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.y3_maxpool.argtypes = [c_void_p, c_void_p] + [c_int32] * 8 + [c_void_p]
+    L.y3_spp3.argtypes = [c_void_p] * 4 + [c_int32] * 6 + [c_void_p]
+    L.y3_add.argtypes = [c_void_p] * 3 + [c_int64] + [c_int32] * 4 + [c_void_p]
+    L.y3_copy_channels.argtypes = [c_void_p] * 2 + [c_int64] + [c_int32] * 3 + [c_void_p]
+    L.y3_upsample2x.argtypes = [c_void_p] * 2 + [c_int32] * 6 + [c_void_p]
+    L.y3_pack_nchw_f32.argtypes = [c_void_p] * 2 + [c_int32] * 5 + [c_void_p]
+    L.y3_pack_bgr_u8.argtypes = [c_void_p] * 2 + [c_int32] * 4 + [c_void_p]
+    L.y3_yolo_decode_dense.argtypes = [POINTER(HeadDesc)] + [c_void_p] * 5
+    L.y3_yolo_decode_cands.argtypes = [POINTER(HeadDesc), c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                       c_int32, c_void_p]
+    L.y3_nms_workspace_bytes.argtypes = [c_int32] * 3
+    L.y3_nms_workspace_bytes.restype = c_size_t
+    L.y3_nms.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_size_t, c_void_p]
+    L.y3_compact_kept.argtypes = [c_void_p] * 3 + [c_int32] * 2 + [c_void_p] * 2 + [c_int32, c_void_p]
+    for name in EXPORTS:
+        if getattr(L, name).restype is ctypes.c_int and name not in ("y3_abi_version",):
+            pass  # int status is ctypes' default restype
+    if L.y3_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libyolov3_b200.so ABI {L.y3_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"libyolov3_b200: {lib().y3_last_error().decode()} (status {rc})")
+
+
+_checked_devices = set()
+
+
+def require_device(device):
+    """Raise unless ``device`` is a CUDA sm_100 device usable by the library."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("yolov3_b200 runs on CUDA sm_100a devices only (no CPU fallback); got device "
+                           f"'{device}'")
+    if not torch.cuda.is_available():
+        raise RuntimeError("yolov3_b200 needs a CUDA device (no CPU fallback) and none is available")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        _check(lib().y3_check_device(idx))
+        _checked_devices.add(idx)
+    return torch.device("cuda", idx)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("yolov3_b200 kernels take CUDA tensors only")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().y3_launch_count())
+
+
+def reset_launch_count():
+    lib().y3_reset_launch_count()
+
+
+# ---- kernels --------------------------------------------------------------------------------
+
+def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, leaky,
+           res_ptr=None, ld_res=0, out_f32=False, upsample2x=False, force_im2col=False):
+    """Raw-pointer form used by the engine plan (views into concat buffers are plain pointers)."""
+    d = ConvDesc(n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, ld_res, int(leaky), int(out_f32),
+                 int(upsample2x), 1 if force_im2col else 0)
+    _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
+
+
+def maxpool(x_ptr, y_ptr, n, h, w, c, ld_x, ld_y, ksize, stride):
+    _check(lib().y3_maxpool(x_ptr, y_ptr, n, h, w, c, ld_x, ld_y, ksize, stride, _stream()))
+
+
+def spp3(x_ptr, y5_ptr, y9_ptr, y13_ptr, n, h, w, c, ld_x, ld_y):
+    _check(lib().y3_spp3(x_ptr, y5_ptr, y9_ptr, y13_ptr, n, h, w, c, ld_x, ld_y, _stream()))
+
+
+def add(a_ptr, b_ptr, y_ptr, pixels, c, ld_a, ld_b, ld_y):
+    _check(lib().y3_add(a_ptr, b_ptr, y_ptr, pixels, c, ld_a, ld_b, ld_y, _stream()))
+
+
+def copy_channels(x_ptr, y_ptr, pixels, c, ld_x, ld_y):
+    _check(lib().y3_copy_channels(x_ptr, y_ptr, pixels, c, ld_x, ld_y, _stream()))
+
+
+def upsample2x(x_ptr, y_ptr, n, h, w, c, ld_x, ld_y):
+    _check(lib().y3_upsample2x(x_ptr, y_ptr, n, h, w, c, ld_x, ld_y, _stream()))
+
+
+def pack_nchw_f32(x, y, c_pad):
+    n, c, h, w = x.shape
+    _check(lib().y3_pack_nchw_f32(_ptr(x), _ptr(y), n, c, h, w, c_pad, _stream()))
+
+
+def pack_bgr_u8(x, y, c_pad):
+    n, h, w, c = x.shape
+    assert c == 3
+    _check(lib().y3_pack_bgr_u8(_ptr(x), _ptr(y), n, h, w, c_pad, _stream()))
+
+
+def make_head_desc(n, g_h, g_w, anchors, num_classes, ld, box_offset, boxes_per_image, train_w, train_h):
+    d = HeadDesc()
+    d.n, d.g_h, d.g_w = n, g_h, g_w
+    d.num_anchors, d.num_classes, d.ld = len(anchors), num_classes, ld
+    d.box_offset, d.boxes_per_image = box_offset, boxes_per_image
+    for i, (aw, ah) in enumerate(anchors):
+        d.anchor_w[i] = float(aw)
+        d.anchor_h[i] = float(ah)
+    d.train_w, d.train_h = float(train_w), float(train_h)
+    return d
+
+
+def yolo_decode_dense(desc, logits, bbox_xywh, class_prob, class_idx):
+    _check(lib().y3_yolo_decode_dense(ctypes.byref(desc), _ptr(logits), _ptr(bbox_xywh), _ptr(class_prob),
+                                      _ptr(class_idx), _stream()))
+
+
+def yolo_decode_cands(desc, logits, prob_thresh, orig_hw, cands, counts, cap):
+    _check(lib().y3_yolo_decode_cands(ctypes.byref(desc), _ptr(logits), float(prob_thresh), _ptr(orig_hw),
+                                      _ptr(cands), _ptr(counts), cap, _stream()))
+
+
+def nms_workspace_bytes(n, cap, num_classes):
+    return int(lib().y3_nms_workspace_bytes(n, cap, num_classes))
+
+
+def nms(cands, counts, n, cap, num_classes, iou_thresh, per_class, sorted_out, keep, class_first_box, workspace):
+    _check(lib().y3_nms(_ptr(cands), _ptr(counts), n, cap, num_classes, float(iou_thresh), int(per_class),
+                        _ptr(sorted_out), _ptr(keep), _ptr(class_first_box), _ptr(workspace),
+                        workspace.numel() * workspace.element_size(), _stream()))
+
+
+def compact_kept(sorted_in, keep, counts, n, cap, dets, det_counts, flat):
+    _check(lib().y3_compact_kept(_ptr(sorted_in), _ptr(keep), _ptr(counts), n, cap, _ptr(dets), _ptr(det_counts),
+                                 int(flat), _stream()))
