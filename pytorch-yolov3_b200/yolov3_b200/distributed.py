@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU, image batches sharded by rank, detections gathered.
+
+The hot path has no exchange step (images are independent through forward, decode and NMS), so
+the only collective is the gather of kept detections after NMS: an
+``all_gather`` of per-image counts followed by an ``all_gather`` of the padded record buffer.
+Works with any ``torch.distributed`` backend: NCCL with CUDA tensors on the B200 box, gloo with
+CPU tensors in the host-logic tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import records_to_numpy
+
+
+def shard_range(num_images, rank, world_size):
+    """Contiguous shard ``[lo, hi)`` of a global batch owned by ``rank`` (remainder spread over
+    the first ranks)."""
+    base, rem = divmod(num_images, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_results(results):
+    """``inference()`` results of the local images -> (records int32 [K,8], counts int64 [B])."""
+    counts = np.asarray([len(r[1]) for r in results], dtype=np.int64)
+    rec = np.zeros((int(counts.sum()), 8), dtype=np.int32)
+    pos = 0
+    for tlbr, prob, cls in results:
+        k = len(prob)
+        rec[pos:pos + k, 0:4] = tlbr
+        rec[pos:pos + k, 4] = np.asarray(prob, dtype=np.float32).view(np.int32)
+        rec[pos:pos + k, 5] = cls
+        pos += k
+    return rec, counts
+
+
+def unpack_results(rec, counts):
+    """Inverse of pack_results."""
+    out, pos = [], 0
+    for k in counts:
+        tlbr, prob, cls, _ = records_to_numpy(rec[pos:pos + int(k)])
+        out.append([tlbr, prob, cls])
+        pos += int(k)
+    return out
+
+
+def gather_detections(rec, counts, group=None, device=None):
+    """All-gather kept detections of every rank.
+
+    Args:
+        rec: this rank's records, int32 ``[K, 8]`` (numpy or tensor), images back to back.
+        counts: records per local image, ``[B_local]``.
+        device: where the collective's tensors live (``cuda:<local_rank>`` for NCCL, ``cpu`` for gloo).
+    Returns:
+        (records int32 numpy [K_total, 8] in global image order, counts int64 numpy [B_total]);
+        ranks may own different numbers of images.
+    """
+    world = dist.get_world_size(group)
+    device = torch.device(device or "cpu")
+    rec_t = torch.as_tensor(np.ascontiguousarray(rec) if isinstance(rec, np.ndarray) else rec).to(device, torch.int32)
+    cnt_t = torch.as_tensor(np.asarray(counts, dtype=np.int64)).to(device)
+    # 1. how many images / records every rank holds
+    meta = torch.tensor([cnt_t.numel(), rec_t.shape[0]], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = torch.stack(metas).cpu().numpy()
+    max_img, max_rec = int(metas[:, 0].max()), int(metas[:, 1].max())
+    # 2. padded counts and records
+    cnt_pad = torch.zeros(max(max_img, 1), dtype=torch.int64, device=device)
+    cnt_pad[:cnt_t.numel()] = cnt_t
+    rec_pad = torch.zeros(max(max_rec, 1), 8, dtype=torch.int32, device=device)
+    rec_pad[:rec_t.shape[0]] = rec_t
+    all_cnt = [torch.zeros_like(cnt_pad) for _ in range(world)]
+    all_rec = [torch.zeros_like(rec_pad) for _ in range(world)]
+    dist.all_gather(all_cnt, cnt_pad, group=group)
+    dist.all_gather(all_rec, rec_pad, group=group)
+    out_cnt = np.concatenate([c.cpu().numpy()[:metas[r, 0]] for r, c in enumerate(all_cnt)])
+    out_rec = np.concatenate([t.cpu().numpy()[:metas[r, 1]] for r, t in enumerate(all_rec)])
+    return out_rec, out_cnt

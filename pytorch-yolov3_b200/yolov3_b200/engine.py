@@ -1,0 +1,490 @@
+"""Execution plan for one (batch, height, width): the host-side "compiler" between the parsed
+cfg and ``libyolov3_b200.so``.
+
+What it decides once, at build time (reference semantics: yolov3/darknet.py:351-405):
+  * NHWC bf16 buffers for every block output that is materialised; YOLO head convolutions
+    write float32 logits.
+  * BatchNorm folded into bf16 weights + fp32 bias (``W' = W*g/sqrt(var+eps)``,
+    ``b' = beta - mean*g/sqrt(var+eps)``), repacked ``[Cout][R][S][Cin]`` for the implicit GEMM.
+  * shortcut (:376-379) fused into the epilogue of the convolution that produces its first
+    operand; nearest x2 upsample (:299-305) fused into the producing convolution's store;
+    route / torch.cat (:369-375) made zero-copy by letting producers write into channel
+    slices of a pre-allocated concat buffer; the three SPP max-pools run as one kernel.
+    When a fusion's precondition fails (the intermediate has another consumer) the plan falls
+    back to the stand-alone CUDA kernel for that block — still device code, never the CPU.
+  * the kernel sequence is captured into CUDA graphs: (input packing + forward + dense decode)
+    for ``Darknet.forward`` and (uint8 packing + forward + fused decode/threshold + NMS +
+    compaction) for ``inference``.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _p(buf):
+    return buf.data_ptr() if buf.is_cuda else 0
+
+
+def _ceil(x, m):
+    return (x + m - 1) // m * m
+
+
+class View:
+    """NHWC tensor view: channel slice ``[c0, c0+C)`` of a buffer with pixel pitch ``ld``."""
+    __slots__ = ("buf", "ptr", "C", "ld", "H", "W", "f32")
+
+    def __init__(self, buf, ptr, C, ld, H, W, f32=False):
+        self.buf, self.ptr, self.C, self.ld, self.H, self.W, self.f32 = buf, ptr, C, ld, H, W, f32
+
+
+class Engine:
+    def __init__(self, net, batch, height, width, device):
+        self.net, self.B, self.H, self.W, self.device = net, batch, height, width, device
+        self.use_graphs = os.environ.get("Y3_NO_GRAPH", "0") != "1"
+        self._graphs = {}
+        self.conv_flops = 0  # algorithmic 2*MAC per batch, no padding credit
+        self.conv_ops = []   # (block, launch closure, flops) for per-kernel timing in bench.py
+        # device "meta" builds the plan without touching a GPU (host-logic tests); it cannot run
+        self.dry = torch.device(device).type == "meta"
+        if self.dry:
+            self._build()
+        else:
+            with torch.cuda.device(device):
+                self._build()
+
+    # ------------------------------------------------------------------------------------
+    # plan construction
+    # ------------------------------------------------------------------------------------
+    def _build(self):
+        net, B, dev = self.net, self.B, self.device
+        blocks = net.blocks
+        nb = len(blocks)
+        cin0 = net.net_info["channels"]
+
+        # ---- shapes of every block output -------------------------------------------------
+        shape = []  # (C, H, W)
+        cur = (cin0, self.H, self.W)
+        for i, b in enumerate(blocks):
+            t = b["type"]
+            if t == "convolutional":
+                k, s = b["size"], b["stride"]
+                pad = (k - 1) // 2 if "pad" in b else 0
+                if k not in (1, 3) or s not in (1, 2):
+                    raise NotImplementedError(f"block {i}: conv size={k} stride={s} not supported (1|3, 1|2)")
+                cur = (b["filters"], (cur[1] + 2 * pad - k) // s + 1, (cur[2] + 2 * pad - k) // s + 1)
+            elif t == "maxpool":
+                k, s = b["size"], b["stride"]
+                if not (k > 1 and s == 1):
+                    cur = (cur[0], (cur[1] - k) // s + 1, (cur[2] - k) // s + 1)
+            elif t == "upsample":
+                if b["stride"] != 2:
+                    raise NotImplementedError(f"block {i}: upsample stride {b['stride']} not supported (2)")
+                cur = (cur[0], cur[1] * 2, cur[2] * 2)
+            elif t == "route":
+                srcs = [shape[j] for j in b["layers"]]
+                if any(s_[1:] != srcs[0][1:] for s_ in srcs):
+                    raise RuntimeError(f"block {i}: route sources have different spatial sizes")
+                cur = (sum(s_[0] for s_ in srcs), srcs[0][1], srcs[0][2])
+            elif t == "shortcut":
+                if shape[i - 1] != shape[i + b["from"]]:
+                    raise RuntimeError(f"block {i}: shortcut operands differ in shape")
+                cur = shape[i - 1]
+            elif t == "yolo":
+                pass
+            else:
+                raise NotImplementedError(f"block {i}: type '{t}' not supported")
+            shape.append(cur)
+
+        # ---- aliases, producers, consumers --------------------------------------------------
+        INPUT = -1
+        alias = {}
+        for i, b in enumerate(blocks):
+            if b["type"] == "yolo":
+                alias[i] = i - 1
+            elif b["type"] == "route" and len(b["layers"]) == 1:
+                alias[i] = b["layers"][0]
+
+        def root(i):
+            while i in alias:
+                i = alias[i]
+            return i
+
+        def inputs_of(i):
+            b = blocks[i]
+            if b["type"] == "route":
+                return [root(j) for j in b["layers"]]
+            if b["type"] == "shortcut":
+                return [root(i - 1), root(i + b["from"])]
+            return [root(i - 1)] if i > 0 else [INPUT]
+
+        consumers = {}
+        for i in range(nb):
+            if i in alias and blocks[i]["type"] != "yolo":
+                continue
+            for r in inputs_of(i):
+                consumers.setdefault(r, []).append(i)
+
+        def is_head(i):
+            return blocks[i]["type"] == "convolutional" and i + 1 < nb and blocks[i + 1]["type"] == "yolo"
+
+        # ---- fusion decisions ---------------------------------------------------------------------
+        fused_into = {}   # conv block -> shortcut / upsample block whose output it writes
+        residual_of = {}  # conv block -> root block providing the residual
+        for i, b in enumerate(blocks):
+            if b["type"] == "shortcut":
+                a, r = root(i - 1), root(i + b["from"])
+                if (a >= 0 and blocks[a]["type"] == "convolutional" and not is_head(a) and consumers.get(a) == [i]
+                        and a != r and a not in fused_into):
+                    fused_into[a] = i
+                    residual_of[a] = r
+            elif b["type"] == "upsample":
+                a = root(i - 1)
+                if (a >= 0 and blocks[a]["type"] == "convolutional" and not is_head(a) and consumers.get(a) == [i]
+                        and a not in fused_into):
+                    fused_into[a] = i
+        fused_blocks = set(fused_into.values())
+
+        # ---- concat placement ------------------------------------------------------------------------
+        placement = {}  # root block -> (route block, channel offset)
+        concat_buf = {}
+        for i, b in enumerate(blocks):
+            if b["type"] == "route" and len(b["layers"]) > 1:
+                C, H, W = shape[i]
+                if C % 8:
+                    raise NotImplementedError(f"block {i}: concat of {C} channels (multiple of 8 required)")
+                concat_buf[i] = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+                off = 0
+                for j in b["layers"]:
+                    r = root(j)
+                    movable = (r >= 0 and r not in placement and r not in concat_buf and not is_head(r)
+                               and off % 8 == 0)
+                    if movable:
+                        placement[r] = (i, off)
+                    off += shape[j][0]
+
+        views = {}
+        self._keep = []  # buffers kept alive
+
+        def alloc(i, f32=False, c_store=None):
+            C, H, W = shape[i]
+            if i in placement and not f32:
+                r, off = placement[i]
+                buf = concat_buf[r]
+                return View(buf, _p(buf) + off * 2, C, buf.shape[3], H, W)
+            cs = c_store or C
+            buf = torch.empty(B, H, W, cs, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+            if cs != C:
+                buf.zero_()
+            self._keep.append(buf)
+            return View(buf, _p(buf), cs, cs, H, W, f32)
+
+        # network input: channels padded to 16 for the tensor-core path
+        cin_pad = _ceil(cin0, 16)
+        in_buf = torch.zeros(B, self.H, self.W, cin_pad, device=dev, dtype=torch.bfloat16)
+        views[INPUT] = View(in_buf, _p(in_buf), cin_pad, cin_pad, self.H, self.W)
+        self.in_view = views[INPUT]
+
+        ops = []          # closures, executed in order
+        self.op_names = []
+
+        def emit(name, fn):
+            ops.append(fn)
+            self.op_names.append(name)
+
+        folded = self._folded_weights
+
+        done = set()
+        heads = []
+        for i, b in enumerate(blocks):
+            t = b["type"]
+            if i in done or i in fused_blocks:
+                continue
+            if t == "convolutional":
+                xin = views[inputs_of(i)[0]]
+                k, s = b["size"], b["stride"]
+                pad = (k - 1) // 2 if "pad" in b else 0
+                head = is_head(i)
+                cout = b["filters"]
+                if head:
+                    if consumers.get(i, []) != [i + 1]:
+                        raise NotImplementedError(f"block {i}: YOLO head conv with extra consumers")
+                    cout_pad = _ceil(cout, 16)
+                else:
+                    if cout % 16:
+                        raise NotImplementedError(f"block {i}: filters={cout} must be a multiple of 16")
+                    cout_pad = cout
+                if xin.C % 16:
+                    raise NotImplementedError(f"block {i}: input channels {xin.C} must be a multiple of 16")
+                tgt = fused_into.get(i, i)
+                up = blocks[tgt]["type"] == "upsample"
+                yv = alloc(tgt, f32=head, c_store=cout_pad if head else None)
+                views[tgt] = yv
+                if tgt != i:
+                    views[i] = yv  # never read (single consumer), kept for introspection
+                res = views[residual_of[i]] if i in residual_of else None
+                w, bias = folded(i, xin.C, cout_pad)
+                kw = dict(n=B, h=xin.H, w_in=xin.W, cin=xin.C, cout=cout_pad, ksize=k, stride=s, pad=pad,
+                          ld_x=xin.ld, ld_y=yv.ld, leaky=b["activation"] == "leaky",
+                          res_ptr=res.ptr if res else None, ld_res=res.ld if res else 0, out_f32=head,
+                          upsample2x=up)
+                fn = (lambda xp=xin.ptr, w=w, bias=bias, yp=yv.ptr, kw=kw: _lib.conv2d(xp, w, bias, yp, **kw))
+                emit(f"conv{i}", fn)
+                ho, wo = shape[i][1], shape[i][2]
+                cin_real = cin0 if inputs_of(i)[0] == INPUT else shape[inputs_of(i)[0]][0]
+                flops = 2 * B * ho * wo * cout * cin_real * k * k
+                self.conv_flops += flops
+                self.conv_ops.append((i, fn, flops))
+                if head:
+                    heads.append((i + 1, yv))
+            elif t == "maxpool":
+                src = inputs_of(i)[0]
+                xin = views[src]
+                k, s = b["size"], b["stride"]
+                if xin.C % 8:
+                    raise NotImplementedError(f"block {i}: maxpool over {xin.C} channels (multiple of 8 required)")
+                # SPP: k5/k9/k13 stride-1 pools of the same tensor -> one kernel
+                trio = None
+                if s == 1 and k == 5:
+                    sib = {blocks[j]["size"]: j for j in range(i + 1, nb)
+                           if blocks[j]["type"] == "maxpool" and blocks[j]["stride"] == 1
+                           and inputs_of(j)[0] == src and blocks[j]["size"] in (9, 13)}
+                    if set(sib) == {9, 13}:
+                        trio = (i, sib[9], sib[13])
+                if trio:
+                    vs = [alloc(j) for j in trio]
+                    for j, v in zip(trio, vs):
+                        views[j] = v
+                        done.add(j)
+                    if len({v.ld for v in vs}) == 1:
+                        emit(f"spp{i}", lambda xp=xin.ptr, a=vs[0].ptr, b_=vs[1].ptr, c=vs[2].ptr, h=xin.H, w=xin.W,
+                             C=xin.C, lx=xin.ld, ly=vs[0].ld: _lib.spp3(xp, a, b_, c, B, h, w, C, lx, ly))
+                    else:
+                        for j, v in zip(trio, vs):
+                            emit(f"maxpool{j}", lambda xp=xin.ptr, yp=v.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld,
+                                 ly=v.ld, kk=blocks[j]["size"]: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, 1))
+                else:
+                    yv = alloc(i)
+                    views[i] = yv
+                    emit(f"maxpool{i}", lambda xp=xin.ptr, yp=yv.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld, ly=yv.ld,
+                         kk=k, ss=s: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, ss))
+            elif t == "upsample":  # not fused: stand-alone kernel
+                xin = views[inputs_of(i)[0]]
+                yv = alloc(i)
+                views[i] = yv
+                emit(f"upsample{i}", lambda xp=xin.ptr, yp=yv.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld, ly=yv.ld:
+                     _lib.upsample2x(xp, yp, B, h, w, C, lx, ly))
+            elif t == "shortcut":  # not fused: stand-alone add
+                a, r = (views[j] for j in inputs_of(i))
+                yv = alloc(i)
+                views[i] = yv
+                emit(f"add{i}", lambda ap=a.ptr, bp=r.ptr, yp=yv.ptr, px=B * a.H * a.W, C=a.C, la=a.ld, lb=r.ld,
+                     ly=yv.ld: _lib.add(ap, bp, yp, px, C, la, lb, ly))
+            elif t == "route":
+                if len(b["layers"]) == 1:
+                    views[i] = views[root(i)]
+                    continue
+                buf = concat_buf[i]
+                off = 0
+                for j in b["layers"]:
+                    r = root(j)
+                    if placement.get(r) != (i, off):  # source lives elsewhere: copy its channels in
+                        sv = views[r]
+                        if sv.f32 or sv.C % 8 or off % 8:
+                            raise NotImplementedError(f"block {i}: cannot concatenate source block {j}")
+                        emit(f"copy{i}_{j}", lambda xp=sv.ptr, yp=_p(buf) + off * 2, px=B * sv.H * sv.W,
+                             C=shape[j][0], lx=sv.ld, ly=buf.shape[3]: _lib.copy_channels(xp, yp, px, C, lx, ly))
+                    off += shape[j][0]
+                views[i] = View(buf, _p(buf), shape[i][0], buf.shape[3], shape[i][1], shape[i][2])
+            elif t == "yolo":
+                views[i] = views[root(i)]
+        self.views = views
+        self.backbone_ops = ops
+        self.num_fused = {"shortcut": len(residual_of), "upsample": len(fused_into) - len(residual_of),
+                          "concat_slices": len(placement)}
+
+        # ---- decode -----------------------------------------------------------------------------------
+        if not heads:
+            raise RuntimeError("cfg has no [yolo] block")
+        self.head_descs = []
+        off = 0
+        M = sum(len(blocks[y]["mask"]) * v.H * v.W for y, v in heads)
+        classes = None
+        for y, v in heads:
+            yb = blocks[y]
+            anchors = [yb["anchors"][m] for m in yb["mask"]]
+            nc = shape[y - 1][0] // len(anchors) - 5
+            classes = nc if classes is None else classes
+            if nc != classes:
+                raise NotImplementedError("YOLO heads with different class counts")
+            d = _lib.make_head_desc(B, v.H, v.W, anchors, nc, v.ld, off, M, net.net_info["width"],
+                                    net.net_info["height"])
+            self.head_descs.append((d, v.buf))
+            off += len(anchors) * v.H * v.W
+        self.M, self.num_classes = M, classes
+
+        # static I/O buffers
+        self.in_f32 = torch.zeros(B, cin0, self.H, self.W, device=dev, dtype=torch.float32)
+        self.in_u8 = torch.zeros(B, self.H, self.W, 3, device=dev, dtype=torch.uint8) if cin0 == 3 else None
+        self.bbox = torch.empty(B, M, 4, device=dev, dtype=torch.float32)
+        self.prob = torch.empty(B, M, device=dev, dtype=torch.float32)
+        self.cidx = torch.empty(B, M, device=dev, dtype=torch.int64)
+        self.cap = M
+        self.orig_hw = torch.zeros(B, 2, device=dev, dtype=torch.int32)
+        self.cands = torch.zeros(B, M, 8, device=dev, dtype=torch.int32)
+        self.counts = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.sorted = torch.zeros(B, M, 8, device=dev, dtype=torch.int32)
+        self.keep = torch.zeros(B, M, device=dev, dtype=torch.uint8)
+        self.dets = torch.zeros(B * M, 8, device=dev, dtype=torch.int32)
+        self.det_counts = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.first_box = torch.zeros(B, classes, device=dev, dtype=torch.int32)
+        ws_bytes = 0 if self.dry else _lib.nms_workspace_bytes(B, M, classes)
+        self.nms_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+
+    def _folded_weights(self, i, cin_store, cout_store):
+        """BN-folded bf16 ``[cout_store][R][S][cin_store]`` weights + fp32 bias of conv block ``i``
+        (shared between plans of one network; a4 in SURVEY.md §8a)."""
+        cache = self.net.__dict__.setdefault("_folded_cache", {})
+        key = (self.net._weights_version, i, cin_store, cout_store, str(self.device))
+        if key in cache:
+            return cache[key]
+        seq = self.net.modules_[i]
+        conv = seq[0]
+        with torch.no_grad():
+            W = conv.weight.detach().to(self.device, torch.float32)
+            if len(seq) > 1 and isinstance(seq[1], torch.nn.BatchNorm2d):
+                bn = seq[1]
+                scale = bn.weight.detach().to(self.device, torch.float32) / torch.sqrt(
+                    bn.running_var.detach().to(self.device, torch.float32) + bn.eps)
+                W = W * scale.view(-1, 1, 1, 1)
+                bias = bn.bias.detach().to(self.device, torch.float32) - \
+                    bn.running_mean.detach().to(self.device, torch.float32) * scale
+            else:
+                bias = conv.bias.detach().to(self.device, torch.float32)
+            cout, cin, k, _ = W.shape
+            Wk = torch.zeros(cout_store, k, k, cin_store, device=self.device, dtype=torch.float32)
+            Wk[:cout, :, :, :cin] = W.permute(0, 2, 3, 1)
+            bf = torch.zeros(cout_store, device=self.device, dtype=torch.float32)
+            bf[:cout] = bias
+            out = (Wk.to(torch.bfloat16).contiguous(), bf.contiguous())
+        # drop entries of older weight versions
+        for k_ in [k_ for k_ in cache if k_[0] != self.net._weights_version]:
+            del cache[k_]
+        cache[key] = out
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------
+    def run_backbone(self):
+        for op in self.backbone_ops:
+            op()
+
+    def _decode_dense(self):
+        for d, logits in self.head_descs:
+            _lib.yolo_decode_dense(d, logits, self.bbox, self.prob, self.cidx)
+
+    def _detect_tail(self, prob_thresh, iou_thresh):
+        self.counts.zero_()
+        for d, logits in self.head_descs:
+            _lib.yolo_decode_cands(d, logits, prob_thresh, self.orig_hw, self.cands, self.counts, self.cap)
+        _lib.nms(self.cands, self.counts, self.B, self.cap, self.num_classes, iou_thresh, 1, self.sorted, self.keep,
+                 self.first_box, self.nms_ws)
+        _lib.compact_kept(self.sorted, self.keep, self.counts, self.B, self.cap, self.dets, self.det_counts, 1)
+
+    def _program(self, key):
+        kind = key[0]
+        if kind == "dense_f32":
+            def fn():
+                _lib.pack_nchw_f32(self.in_f32, self.in_view.buf, self.in_view.C)
+                self.run_backbone()
+                self._decode_dense()
+        elif kind == "det_u8":
+            def fn():
+                _lib.pack_bgr_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                self.run_backbone()
+                self._detect_tail(key[1], key[2])
+        elif kind == "det_f32":
+            def fn():
+                _lib.pack_nchw_f32(self.in_f32, self.in_view.buf, self.in_view.C)
+                self.run_backbone()
+                self._detect_tail(key[1], key[2])
+        else:
+            raise KeyError(kind)
+        return fn
+
+    def launch(self, key):
+        """Run program ``key`` on the current stream (CUDA-graph replay after the first call)."""
+        if self.dry:
+            raise RuntimeError("this plan was built on the meta device and cannot run")
+        ent = self._graphs.get(key)
+        if ent is None:
+            fn = self._program(key)
+            with torch.cuda.device(self.device):
+                _lib.reset_launch_count()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    fn()  # warm-up: sets kernel attributes, resolves driver entry points
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                launches = _lib.launch_count() + (1 if key[0].startswith("det") else 0)  # + counts.zero_()
+                graph = None
+                if self.use_graphs:
+                    torch.cuda.synchronize(self.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        fn()
+            ent = (fn, graph, launches)
+            self._graphs[key] = ent
+        fn, graph, _ = ent
+        if graph is not None:
+            graph.replay()
+        else:
+            fn()
+
+    def launches(self, key):
+        """Kernels launched by one run of program ``key`` (bench.py's gpu_launches)."""
+        return self._graphs[key][2]
+
+    # -- Darknet.forward ---------------------------------------------------------------------
+    def forward_dense(self, x):
+        with torch.cuda.device(self.device):
+            self.in_f32.copy_(x.to(torch.float32), non_blocking=True)
+            self.launch(("dense_f32",))
+            return {"bbox_xywh": self.bbox.clone(), "class_prob": self.prob.clone(), "class_idx": self.cidx.clone()}
+
+    # -- inference ------------------------------------------------------------------------------
+    def detect(self, prob_thresh, iou_thresh, kind="det_u8"):
+        """Run the fused detection program on whatever the static input buffer holds; results
+        stay on the device: ``dets`` (flat y3_cand records of all images, image after image),
+        ``det_counts`` [B], ``first_box`` [B, classes]."""
+        with torch.cuda.device(self.device):
+            self.launch((kind, float(prob_thresh), float(iou_thresh)))
+        return self.dets, self.det_counts, self.first_box
+
+    def time_convs(self, iters=3):
+        """CUDA-event time of every convolution launch run eagerly (for bench.py's roofline
+        block): returns (total seconds per forward, [(block, seconds, flops)])."""
+        with torch.cuda.device(self.device):
+            per = []
+            for blk, fn, flops in self.conv_ops:
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                per.append((blk, e0.elapsed_time(e1) * 1e-3 / iters, flops))
+            return sum(p[1] for p in per), per
+
+
+def records_to_numpy(rec):
+    """int32 [K,8] y3_cand records -> (tlbr int64 [K,4], prob float32 [K], cls int64 [K], box int64 [K])."""
+    rec = np.ascontiguousarray(rec)
+    tlbr = rec[:, 0:4].astype(np.int64)
+    prob = rec[:, 4].copy().view(np.float32)
+    return tlbr, prob, rec[:, 5].astype(np.int64), rec[:, 6].astype(np.int64)

@@ -1,0 +1,165 @@
+"""Inference entry points — host-side mirror of the hot-path half of ``yolov3/inference.py`` of
+nrsyed/pytorch-yolov3 (``inference`` :286-368, ``non_max_suppression`` :220-266,
+``cxywh_to_tlbr`` :269-283), with identical argument meaning, threshold semantics
+(keep ``prob >= prob_thresh``, suppress ``iou > nms_iou_thresh``) and return structures.
+
+Everything between the uint8 images and the kept detections runs on the GPU in one CUDA-graph
+replay: BGR->RGB /255 packing, the Darknet forward, YOLO decode + threshold + pixel scaling +
+integer truncation + tl/br conversion, per-class NMS and compaction.  The host copies the
+images up (pinned memory), copies the kept records down, and re-orders class groups the way the
+reference's ``set(class_idx)`` loop visits them.  There is no CPU implementation here.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import records_to_numpy
+
+
+def cxywh_to_tlbr(bbox_xywh):
+    """``(cx, cy, w, h, ...) -> (x1, y1, x2, y2, ...)`` with ``tl = c - wh // 2`` and
+    ``br = c + wh // 2``; extra columns pass through (reference: yolov3/inference.py:269-283).
+    Pure index arithmetic on the caller's host array (the fused GPU decode does the same
+    conversion on device for ``inference``)."""
+    bbox_tlbr = np.copy(bbox_xywh)
+    half = bbox_xywh[:, 2:4] // 2
+    bbox_tlbr[:, :2] = bbox_xywh[:, :2] - half
+    bbox_tlbr[:, 2:4] = bbox_xywh[:, :2] + half
+    return bbox_tlbr
+
+
+def _set_order(first_box_row):
+    """Classes in the order the reference's ``for class_ in set(class_idx)`` loop visits them
+    (yolov3/inference.py:247-250).  A Python set's iteration order depends only on the hashes and
+    on the order in which DISTINCT keys were inserted, i.e. on each class's first occurrence in
+    candidate order — which is ascending box index, recorded on the device by ``y3_nms``."""
+    present = np.nonzero(first_box_row != np.iinfo(np.int32).max)[0]
+    by_first_seen = present[np.argsort(first_box_row[present], kind="stable")]
+    return list(set(np.int64(c) for c in by_first_seen))
+
+
+def _order_like_reference(cls_sorted, first_box_row):
+    """Permutation taking records sorted by (class asc, prob desc) to the reference's output
+    order: class groups in ``set()`` order, prob descending inside a group."""
+    if cls_sorted.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    order = _set_order(first_box_row)
+    starts = np.searchsorted(cls_sorted, order, side="left")
+    ends = np.searchsorted(cls_sorted, order, side="right")
+    return np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if order else np.zeros(0, np.int64)
+
+
+def _pinned(shape, dtype):
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True):
+    """Run the network on image(s); same contract as the reference (yolov3/inference.py:286-368).
+
+    Args:
+        net: ``yolov3_b200.Darknet``.
+        images: one ``HxWx3`` uint8 BGR array or a list of them (one batch).
+        device: CUDA device string; must be the device ``net`` runs on.
+        prob_thresh: detections with ``class_prob >= prob_thresh`` are kept.
+        nms_iou_thresh: per-class NMS suppresses boxes with ``iou > nms_iou_thresh``.
+        resize: resize every image to the cfg's ``[net]`` size first (cv2 bilinear, as the
+            reference does); otherwise all images must already share one shape.
+
+    Returns:
+        list (one entry per image) of ``[bbox_tlbr int64 (K,4), class_prob float32 (K,),
+        class_idx int64 (K,)]`` in ORIGINAL-image pixels, unclipped, ordered like the reference.
+    """
+    if not isinstance(images, list):
+        images = [images]
+    dev = _lib.require_device(device)
+    orig_shapes = [im.shape for im in images]
+    if resize:
+        import cv2
+        net_shape = (net.net_info["height"], net.net_info["width"])
+        images = [cv2.resize(im, net_shape) if im.shape[:2] != net_shape else im for im in images]
+    batch = np.stack(images)  # raises ValueError on ragged shapes, like the reference
+    if batch.dtype != np.uint8 or batch.ndim != 4 or batch.shape[3] != 3:
+        raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got {batch.dtype} {batch.shape}")
+    B, H, W, _ = batch.shape
+    eng = net.engine(B, H, W)
+    if eng.device != dev:
+        raise RuntimeError(f"net runs on {eng.device}, inference(device='{device}') requested")
+
+    with torch.cuda.device(dev):
+        io = eng.__dict__.setdefault("_host_io", {})
+        if not io:
+            io["img"] = _pinned((B, H, W, 3), torch.uint8)
+            io["hw"] = _pinned((B, 2), torch.int32)
+            io["counts"] = _pinned((B,), torch.int32)
+            io["first"] = _pinned((B, eng.num_classes), torch.int32)
+            io["dets"] = _pinned((B * eng.cap, 8), torch.int32)
+        io["img"].numpy()[...] = batch
+        io["hw"].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
+        eng.in_u8.copy_(io["img"], non_blocking=True)
+        eng.orig_hw.copy_(io["hw"], non_blocking=True)
+        dets, det_counts, first_box = eng.detect(prob_thresh, nms_iou_thresh, "det_u8")
+        io["counts"].copy_(det_counts, non_blocking=True)
+        io["first"].copy_(first_box, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        counts = io["counts"].numpy().astype(np.int64)
+        total = int(counts.sum())
+        if total:
+            io["dets"][:total].copy_(dets[:total], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        rec = io["dets"].numpy()[:total]
+        first = io["first"].numpy()
+
+    results, pos = [], 0
+    for i in range(B):
+        tlbr, prob, cls, _ = records_to_numpy(rec[pos:pos + counts[i]])
+        pos += counts[i]
+        perm = _order_like_reference(cls, first[i])
+        results.append([tlbr[perm, :], prob[perm], cls[perm]])
+    return results
+
+
+def non_max_suppression(bbox_tlbr, class_prob, class_idx=None, iou_thresh=0.3):
+    """Greedy NMS on the GPU; returns the kept indices exactly as the reference does
+    (yolov3/inference.py:220-266): per class in ``set(class_idx)`` order when ``class_idx`` is
+    given (descending probability inside a class), class-agnostic otherwise.
+
+    Args:
+        bbox_tlbr: ``Mx4`` integer array (x1, y1, x2, y2); |coordinates| < 2**31.
+        class_prob: ``M`` probabilities.
+        class_idx: ``M`` class indices in ``[0, 1024)`` or ``None``.
+        iou_thresh: boxes with ``iou > iou_thresh`` w.r.t. a kept box are dropped.
+    """
+    dev = _lib.require_device("cuda")
+    bbox_tlbr = np.asarray(bbox_tlbr)
+    n = int(bbox_tlbr.shape[0])
+    if n == 0:
+        return []
+    class_prob = np.asarray(class_prob, dtype=np.float32)
+    per_class = class_idx is not None
+    cls = np.asarray(class_idx, dtype=np.int64) if per_class else np.zeros(n, dtype=np.int64)
+    if per_class and (cls.min() < 0 or cls.max() >= 1024):
+        raise ValueError("class_idx must lie in [0, 1024)")
+    if np.abs(bbox_tlbr[:, :4]).max() >= 2 ** 31:
+        raise ValueError("box coordinates must fit in int32")
+    num_classes = int(cls.max()) + 1
+    rec = np.zeros((1, n, 8), dtype=np.int32)
+    rec[0, :, 0:4] = bbox_tlbr[:, :4]
+    rec[0, :, 4] = class_prob.view(np.int32)
+    rec[0, :, 5] = cls
+    rec[0, :, 6] = np.arange(n)
+    with torch.cuda.device(dev):
+        cands = torch.from_numpy(rec).to(dev)
+        counts = torch.tensor([n], dtype=torch.int32, device=dev)
+        sorted_ = torch.empty_like(cands)
+        keep = torch.zeros(1, n, dtype=torch.uint8, device=dev)
+        first = torch.empty(1, num_classes, dtype=torch.int32, device=dev)
+        ws = torch.empty(_lib.nms_workspace_bytes(1, n, num_classes), dtype=torch.uint8, device=dev)
+        _lib.nms(cands, counts, 1, n, num_classes, iou_thresh, per_class, sorted_, keep, first, ws)
+        srt = sorted_[0].cpu().numpy()
+        kp = keep[0].cpu().numpy().astype(bool)
+        first = first[0].cpu().numpy()
+    kept = srt[kp]
+    if not per_class:
+        return [int(v) for v in kept[:, 6]]
+    perm = _order_like_reference(kept[:, 5].astype(np.int64), first)
+    return [int(v) for v in kept[perm, 6]]

@@ -1,0 +1,521 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(ctypes) and through the package API, against the CPU oracle and the committed golden vectors.
+
+Bars (BASELINE.json north_star):
+  * convolutions (bf16 tensor cores, fp32 accumulate): max|d| / max|ref| <= 1e-2 per layer,
+    teacher-forced (each layer fed the same input as the oracle);
+  * max-pool / concat / upsample / packing: exact on bf16 values;
+  * decode: float fields within 2e-6 relative of the oracle on identical logits, class ids
+    equal, integer boxes equal except where a float lands within an ulp of an integer
+    (counted, must stay under 0.2 %);
+  * NMS: kept indices bit-exact, including order, on identical candidates.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import yolov3_b200
+from yolov3_b200 import _lib
+from oracle import darknet_oracle as DO
+from oracle import nms_c
+from oracle import postprocess_oracle as PO
+from conftest import GOLDEN, MODELS
+
+pytestmark = pytest.mark.gpu
+CONV_TOL = 1e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(dev(), torch.bfloat16)
+
+
+def fold(prm, cin_store, cout_store):
+    """Test-side BN fold (fp32) + repack, independent of the engine's."""
+    W = prm["weight"].float()
+    if "bn_bias" in prm:
+        scale = prm["bn_weight"] / torch.sqrt(prm["bn_var"] + DO.BN_EPS)
+        W = W * scale.view(-1, 1, 1, 1)
+        b = prm["bn_bias"] - prm["bn_mean"] * scale
+    else:
+        b = prm["bias"]
+    cout, cin, k, _ = W.shape
+    Wk = torch.zeros(cout_store, k, k, cin_store)
+    Wk[:cout, :, :, :cin] = W.permute(0, 2, 3, 1)
+    bf = torch.zeros(cout_store)
+    bf[:cout] = b
+    return Wk.to(dev(), torch.bfloat16).contiguous(), bf.to(dev()).contiguous()
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max() / ref.abs().max())
+
+
+# ------------------------------------------------------------------------------------------
+# a5: convolution blocks, teacher-forced, golden vectors from the reference's own modules
+# ------------------------------------------------------------------------------------------
+def test_conv_blocks_against_reference_goldens():
+    z = np.load(os.path.join(GOLDEN, "conv_blocks.npz"))
+    n = 0
+    while f"c{n}_meta" in z:
+        cin, cout, k, s, bn, leaky, H = (int(v) for v in z[f"c{n}_meta"])
+        prm = {key: torch.from_numpy(z[f"c{n}_{key}"]) for key in
+               ("weight", "bias", "bn_weight", "bn_bias", "bn_mean", "bn_var") if f"c{n}_{key}" in z}
+        x = torch.from_numpy(z[f"c{n}_x"])
+        ref = torch.from_numpy(z[f"c{n}_y"])
+        cout_store = (cout + 15) // 16 * 16
+        w, b = fold(prm, cin, cout_store)
+        xin = nhwc_bf16(x)
+        f32 = not bn  # head-style block: float32 output
+        y = torch.empty(x.shape[0], ref.shape[2], ref.shape[3], cout_store, device=dev(),
+                        dtype=torch.float32 if f32 else torch.bfloat16)
+        for force in (False, True):
+            y.zero_()
+            _lib.conv2d(xin.data_ptr(), w, b, y.data_ptr(), n=x.shape[0], h=H, w_in=H, cin=cin, cout=cout_store,
+                        ksize=k, stride=s, pad=(k - 1) // 2, ld_x=cin, ld_y=cout_store, leaky=bool(leaky),
+                        out_f32=f32, force_im2col=force)
+            torch.cuda.synchronize()
+            got = y.float().cpu().permute(0, 3, 1, 2)[:, :cout]
+            assert rel_err(got, ref) <= CONV_TOL, (n, force, rel_err(got, ref))
+        n += 1
+    assert n == 6
+
+
+def test_conv_fused_shortcut_upsample_and_concat_slice():
+    g = torch.Generator().manual_seed(21)
+    n, cin, cout, H = 2, 64, 32, 10
+    x = torch.randn(n, cin, H, H, generator=g)
+    prm = {"weight": torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5,
+           "bias": torch.randn(cout, generator=g) * 0.1}
+    res = torch.randn(n, cout, H, H, generator=g)
+    w, b = fold(prm, cin, cout)
+    xb, rb = nhwc_bf16(x), nhwc_bf16(res)
+    xr, rr = xb.float().cpu().permute(0, 3, 1, 2), rb.float().cpu().permute(0, 3, 1, 2)
+    conv = F.leaky_relu(F.conv2d(xr, prm["weight"].bfloat16().float(), prm["bias"], padding=1), 0.1)
+    # shortcut fused, written into channels [16, 48) of a 64-channel concat buffer
+    buf = torch.zeros(n, H, H, 64, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(xb.data_ptr(), w, b, buf.data_ptr() + 16 * 2, n=n, h=H, w_in=H, cin=cin, cout=cout, ksize=3, stride=1,
+                pad=1, ld_x=cin, ld_y=64, leaky=True, res_ptr=rb.data_ptr(), ld_res=cout)
+    torch.cuda.synchronize()
+    got = buf.float().cpu().permute(0, 3, 1, 2)
+    assert rel_err(got[:, 16:48], conv + rr) <= CONV_TOL
+    assert float(got[:, :16].abs().max()) == 0 and float(got[:, 48:].abs().max()) == 0  # neighbours untouched
+    # upsample fused
+    up = torch.zeros(n, 2 * H, 2 * H, cout, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(xb.data_ptr(), w, b, up.data_ptr(), n=n, h=H, w_in=H, cin=cin, cout=cout, ksize=3, stride=1, pad=1,
+                ld_x=cin, ld_y=cout, leaky=True, upsample2x=True)
+    torch.cuda.synchronize()
+    got = up.float().cpu().permute(0, 3, 1, 2)
+    assert rel_err(got, F.interpolate(conv, scale_factor=2, mode="nearest")) <= CONV_TOL
+    assert torch.equal(got[:, :, 0::2, 0::2], got[:, :, 1::2, 1::2])
+
+
+def test_conv_rejects_bad_arguments():
+    t = torch.zeros(16, device=dev(), dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="cin"):
+        _lib.conv2d(t.data_ptr(), t, t.float(), t.data_ptr(), n=1, h=4, w_in=4, cin=3, cout=16, ksize=3, stride=1,
+                    pad=1, ld_x=8, ld_y=16, leaky=True)
+    with pytest.raises(RuntimeError, match="ksize"):
+        _lib.conv2d(t.data_ptr(), t, t.float(), t.data_ptr(), n=1, h=4, w_in=4, cin=16, cout=16, ksize=5, stride=1,
+                    pad=2, ld_x=16, ld_y=16, leaky=True)
+
+
+# ------------------------------------------------------------------------------------------
+# a6: max-pool (zero right/bottom padding), golden vectors
+# ------------------------------------------------------------------------------------------
+def test_maxpool_goldens_exact_on_bf16_values():
+    z = np.load(os.path.join(GOLDEN, "maxpool.npz"))
+    n = 0
+    while f"p{n}_meta" in z:
+        k, s = (int(v) for v in z[f"p{n}_meta"])
+        x = torch.from_numpy(z[f"p{n}_x"]).bfloat16().float()  # the values the kernel sees
+        ref = DO.maxpool_block(x, {"size": k, "stride": s})
+        m = yolov3_b200.MaxPool2d(kernel_size=k, stride=s)
+        got = m(x.to(dev())).cpu()
+        assert torch.equal(got, ref), n
+        n += 1
+
+
+def test_spp_matches_three_pools():
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(2, 32, 19, 19, generator=g) - 0.5).bfloat16()
+    xin = nhwc_bf16(x.float())
+    buf = torch.zeros(2, 19, 19, 128, device=dev(), dtype=torch.bfloat16)
+    buf[..., 96:] = xin
+    p = buf.data_ptr()
+    _lib.spp3(p + 96 * 2, p + 64 * 2, p + 32 * 2, p, 2, 19, 19, 32, 128, 128)
+    torch.cuda.synchronize()
+    ref = torch.cat([DO.maxpool_block(x.float(), {"size": k, "stride": 1}) for k in (13, 9, 5)] + [x.float()], 1)
+    assert torch.equal(buf.float().cpu().permute(0, 3, 1, 2), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# a10: YOLO decode on the reference's golden logits
+# ------------------------------------------------------------------------------------------
+def test_yolo_layer_against_reference_goldens():
+    z = np.load(os.path.join(GOLDEN, "yolo_decode.npz"))
+    anchors = z["anchors"].tolist()
+    n = 0
+    while f"y{n}_x" in z:
+        layer = yolov3_b200.YOLOLayer(anchors, z[f"y{n}_mask"].tolist(), device="cuda")
+        b, p, i = layer(torch.from_numpy(z[f"y{n}_x"]).to(dev()))
+        assert np.allclose(b.cpu().numpy(), z[f"y{n}_bbox"], rtol=2e-6, atol=1e-9)
+        assert np.allclose(p.cpu().numpy(), z[f"y{n}_prob"], rtol=2e-6, atol=1e-12)
+        assert np.array_equal(i.cpu().numpy(), z[f"y{n}_idx"]) and i.dtype == torch.int64
+        n += 1
+    assert n == 4
+
+
+# ------------------------------------------------------------------------------------------
+# a15/a16: NMS, bit-exact kept indices (order included) on the reference's golden cases
+# ------------------------------------------------------------------------------------------
+def test_nms_goldens_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "nms.npz"))
+    for n in range(int(z["num_cases"][0])):
+        tlbr, prob, cls = z[f"n{n}_tlbr"], z[f"n{n}_prob"], z[f"n{n}_cls"]
+        per_class = bool(z[f"n{n}_meta"][2])
+        thr = float(z[f"n{n}_thr"][0])
+        got = yolov3_b200.non_max_suppression(tlbr, prob, cls if per_class else None, thr)
+        assert got == z[f"n{n}_keep"].tolist(), n
+
+
+def stress_candidates(rng, n=10647, classes=80, size=416):
+    """SURVEY.md §8d config 4 recipe: tie-free scores, boxes via cxywh_to_tlbr."""
+    cx, cy = rng.uniform(0, size, n), rng.uniform(0, size, n)
+    w, h = size * (0.02 + 0.4 * rng.random(n)), size * (0.02 + 0.4 * rng.random(n))
+    tlbr = PO.cxywh_to_tlbr(np.stack([cx, cy, w, h], 1).astype(np.int64))
+    prob = rng.permutation(np.linspace(0.01, 0.99, n, dtype=np.float32))
+    assert np.unique(prob).size == n
+    return tlbr, prob, rng.integers(0, classes, n).astype(np.int64)
+
+
+def test_nms_stress_batch_bit_exact_vs_c_oracle():
+    """Config 4 of BASELINE.json at full per-image size (10,647 candidates x 80 classes),
+    batch 256 on the device; every image compared with the C oracle."""
+    B, n, classes = 256, 10647, 80
+    rec = np.zeros((B, n, 8), dtype=np.int32)
+    inputs = []
+    for i in range(B):
+        tlbr, prob, cls = stress_candidates(np.random.default_rng(1000 + i), n, classes)
+        inputs.append((tlbr, prob, cls))
+        rec[i, :, 0:4], rec[i, :, 4], rec[i, :, 5], rec[i, :, 6] = tlbr, prob.view(np.int32), cls, np.arange(n)
+    d = dev()
+    cands = torch.from_numpy(rec).to(d)
+    counts = torch.full((B,), n, dtype=torch.int32, device=d)
+    srt, keep = torch.empty_like(cands), torch.zeros(B, n, dtype=torch.uint8, device=d)
+    first = torch.empty(B, classes, dtype=torch.int32, device=d)
+    ws = torch.empty(_lib.nms_workspace_bytes(B, n, classes), dtype=torch.uint8, device=d)
+    _lib.nms(cands, counts, B, n, classes, 0.3, 1, srt, keep, first, ws)
+    torch.cuda.synchronize()
+    srt, keep = srt.cpu().numpy(), keep.cpu().numpy().astype(bool)
+    for i in range(B):
+        tlbr, prob, cls = inputs[i]
+        want = nms_c.nms(tlbr, prob, cls, 0.3)  # reference order: set(class) groups, prob desc
+        kept = srt[i][keep[i]]
+        # device order is (class asc, prob desc); with >= 80 candidates/class present the
+        # reference's set order is ascending too — compare as ordered lists per class
+        got = kept[:, 6].tolist()
+        assert sorted(got) == sorted(want), i
+        by_cls_got = {c: [b for b, cc in zip(got, kept[:, 5]) if cc == c] for c in range(classes)} if i < 4 else None
+        if by_cls_got:
+            pos = 0
+            for c in list(set(cls)):
+                k = len(by_cls_got[int(c)])
+                assert want[pos:pos + k] == by_cls_got[int(c)]
+                pos += k
+    # idempotence: suppressing the kept set again keeps everything
+    i = 0
+    kept = srt[i][keep[i]]
+    again = yolov3_b200.non_max_suppression(kept[:, 0:4].astype(np.int64), kept[:, 4].copy().view(np.float32),
+                                            kept[:, 5].astype(np.int64), 0.3)
+    assert sorted(again) == list(range(len(kept)))
+
+
+def test_nms_class_agnostic_large_segment():
+    tlbr, prob, cls = stress_candidates(np.random.default_rng(77), 3000, 80)
+    assert yolov3_b200.non_max_suppression(tlbr, prob, None, 0.45) == nms_c.nms(tlbr, prob, None, 0.45)
+
+
+def test_nms_edge_cases():
+    assert yolov3_b200.non_max_suppression(np.zeros((0, 4), np.int64), np.zeros(0, np.float32)) == []
+    one = np.array([[3, 4, 10, 12]], np.int64)
+    assert yolov3_b200.non_max_suppression(one, np.array([0.5], np.float32), np.array([7])) == [0]
+    # negative (unclipped) coordinates and identical boxes
+    tlbr = np.array([[-20, -10, 5, 5], [-20, -10, 5, 5], [100, 100, 120, 130]], np.int64)
+    prob = np.array([0.2, 0.9, 0.5], np.float32)
+    assert yolov3_b200.non_max_suppression(tlbr, prob, None, 0.3) == PO.nms(tlbr, prob, None, 0.3) == [1, 2]
+
+
+# ------------------------------------------------------------------------------------------
+# whole network on micro.cfg: every block type, goldens from the reference's Darknet
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def micro():
+    net = yolov3_b200.Darknet(os.path.join(GOLDEN, "micro.cfg"), device="cuda:0")
+    return net.load_weights(os.path.join(GOLDEN, "micro.weights")).eval()
+
+
+def view_to_nchw(v, B):
+    """Read an engine View back as float32 NCHW on the host."""
+    t = v.buf
+    full = t.float().cpu() if t.dtype != torch.float32 else t.cpu()
+    c0 = (v.ptr - t.data_ptr()) // t.element_size()
+    return full.reshape(B, v.H, v.W, -1)[..., c0:c0 + v.C].permute(0, 3, 1, 2).contiguous()
+
+
+def test_micro_network_blocks_and_outputs(micro):
+    z = np.load(os.path.join(GOLDEN, "micro_forward.npz"))
+    x = torch.from_numpy(z["x"])
+    out = micro.forward(x.to(dev()))
+    assert out["bbox_xywh"].shape == (2, 960, 4) and out["class_idx"].dtype == torch.int64
+    eng = micro.engine(2, 64, 64)
+    worst = 0.0
+    for key in z.files:
+        if not key.startswith("block"):
+            continue
+        i = int(key[5:])
+        b = micro.blocks[i]
+        if i not in eng.views or b["type"] not in ("convolutional", "maxpool"):
+            continue
+        ref = torch.from_numpy(z[key])
+        if b["type"] == "convolutional" and (micro.blocks[i + 1]["type"] in ("shortcut", "upsample")):
+            continue  # fused: the stored tensor is the shortcut / upsample output (checked via later blocks)
+        got = view_to_nchw(eng.views[i], 2)[:, :ref.shape[1]]
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        assert e <= 3e-2, (i, e)  # free-running (not teacher-forced) through <= 12 bf16 layers
+    print(f"micro: worst free-running block error {worst:.4f}")
+    # decoded outputs (free-running): probabilities close in absolute terms
+    assert float((out["class_prob"].cpu() - torch.from_numpy(z["class_prob"])).abs().max()) < 0.08
+    agree = float((out["class_idx"].cpu() == torch.from_numpy(z["class_idx"])).float().mean())
+    assert agree > 0.97
+
+
+def test_micro_network_teacher_forced_convs(micro):
+    """Gate (i): every convolution fed exactly the oracle's input for that block."""
+    z = np.load(os.path.join(GOLDEN, "micro_forward.npz"))
+    blocks, net_info = DO.load_model(os.path.join(GOLDEN, "micro.cfg"))
+    _, params = DO.read_weights(os.path.join(GOLDEN, "micro.weights"), blocks, net_info)
+    cap = {}
+    with torch.no_grad():
+        DO.forward(torch.from_numpy(z["x"]), blocks, net_info, params, capture=cap)
+    for i, b in enumerate(blocks):
+        if b["type"] != "convolutional" or i == 0:
+            continue
+        xin = cap[i - 1]
+        ref = cap[i]
+        cin, cout = xin.shape[1], ref.shape[1]
+        cs = (cout + 15) // 16 * 16
+        w, bias = fold(params[i], cin, cs)
+        k, s, pad, bn, leaky = DO.conv_geometry(b)
+        y = torch.empty(2, ref.shape[2], ref.shape[3], cs, device=dev(), dtype=torch.float32)
+        xb = nhwc_bf16(xin)
+        _lib.conv2d(xb.data_ptr(), w, bias, y.data_ptr(), n=2, h=xin.shape[2], w_in=xin.shape[3], cin=cin, cout=cs,
+                    ksize=k, stride=s, pad=pad, ld_x=cin, ld_y=cs, leaky=leaky, out_f32=True)
+        torch.cuda.synchronize()
+        got = y.cpu().permute(0, 3, 1, 2)[:, :cout]
+        assert rel_err(got, ref) <= CONV_TOL, (i, rel_err(got, ref))
+
+
+def oracle_tail_from_engine_logits(net, eng, orig_shapes, prob_thresh, iou):
+    """Decode + post-process + NMS on the CPU oracle from the engine's OWN head logits."""
+    boxes, probs, idxs = [], [], []
+    yolo_blocks = [b for b in net.blocks if b["type"] == "yolo"]
+    for (d, logits), yb in zip(eng.head_descs, yolo_blocks):
+        anchors = [yb["anchors"][m] for m in yb["mask"]]
+        fields = len(anchors) * (5 + eng.num_classes)
+        x = logits.cpu()[..., :fields].permute(0, 3, 1, 2).contiguous()
+        b, p, i = DO.yolo_decode(x, anchors)
+        boxes.append(b), probs.append(p), idxs.append(i)
+    bbox = torch.cat(boxes, 1)
+    bbox[:, :, 2:4] = bbox[:, :, 2:4] / torch.tensor([net.net_info["width"], net.net_info["height"]])
+    return bbox, torch.cat(probs, 1), torch.cat(idxs, 1), PO.postprocess(
+        bbox.numpy().copy(), torch.cat(probs, 1).numpy(), torch.cat(idxs, 1).numpy(), orig_shapes, prob_thresh, iou)
+
+
+def compare_detection_lists(got, want):
+    """Returns (#exactly equal images, total mismatching detections, total detections)."""
+    equal, bad, tot = 0, 0, 0
+    for g, w in zip(got, want):
+        tot += len(w[1])
+        if all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(g, w)):
+            equal += 1
+            continue
+        gs = {tuple(t) + (int(c),) for t, c in zip(g[0].tolist(), g[2])}
+        ws = {tuple(t) + (int(c),) for t, c in zip(w[0].tolist(), w[2])}
+        bad += len(gs ^ ws)
+    return equal, bad, tot
+
+
+def test_micro_inference_tail_is_exact_on_identical_logits(micro):
+    """Gates (ii)+(iii): decode + threshold + scaling + truncation + NMS + output order, against
+    the oracle fed the engine's own float32 head logits."""
+    z = np.load(os.path.join(GOLDEN, "micro_inference.npz"))
+    imgs = list(z["images"])
+    res = yolov3_b200.inference(micro, imgs, device="cuda:0", prob_thresh=0.3, nms_iou_thresh=0.3, resize=False)
+    eng = micro.engine(2, 64, 64)
+    *_, want = oracle_tail_from_engine_logits(micro, eng, [im.shape for im in imgs], 0.3, 0.3)
+    for r in res:
+        assert r[0].dtype == np.int64 and r[1].dtype == np.float32 and r[2].dtype == np.int64
+    equal, bad, tot = compare_detection_lists(res, want)
+    print(f"micro tail: {equal}/2 images identical incl. order, {bad} of {tot} detections differ")
+    assert bad <= max(2, 0.002 * tot)
+    # and against the reference's end-to-end golden (fp32 everywhere): report + loose gate
+    gold = [[z[f"img{i}_tlbr"], z[f"img{i}_prob"], z[f"img{i}_cls"]] for i in range(2)]
+    _, bad2, tot2 = compare_detection_lists(res, gold)
+    print(f"micro e2e vs fp32 reference golden: {bad2} of {tot2} detections differ")
+    assert bad2 <= 0.25 * tot2
+
+
+def test_inference_argument_semantics(micro):
+    img = np.random.default_rng(3).integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    one = yolov3_b200.inference(micro, img, device="cuda:0", prob_thresh=0.3, resize=False)  # bare ndarray accepted
+    assert len(one) == 1 and len(one[0]) == 3
+    hi = yolov3_b200.inference(micro, [img], device="cuda:0", prob_thresh=0.9, resize=False)
+    assert len(hi[0][1]) <= len(one[0][1]) and (hi[0][1] >= 0.9).all()
+    with pytest.raises(ValueError):  # ragged batch without resize, like np.stack in the reference
+        yolov3_b200.inference(micro, [img, img[:32]], device="cuda:0", resize=False)
+    # resize=True brings a non-network-size image to the cfg size; boxes come back in ORIGINAL pixels
+    big = np.random.default_rng(4).integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    r = yolov3_b200.inference(micro, [big], device="cuda:0", prob_thresh=0.3, resize=True)
+    assert r[0][0].shape[1] == 4
+
+
+# ------------------------------------------------------------------------------------------
+# full-size networks with calibrated synthetic weights
+# ------------------------------------------------------------------------------------------
+def build_full(name, size, tmp_path_factory):
+    cfg = os.path.join(MODELS, name + ".cfg")
+    blocks, net_info = DO.load_model(cfg)
+    with torch.no_grad():
+        params = DO.synth_params(blocks, net_info, size, seed=1234)
+    wpath = str(tmp_path_factory.mktemp("w") / (name + ".weights"))
+    DO.write_weights(wpath, params, blocks, net_info)
+    net = yolov3_b200.Darknet(cfg, device="cuda:0").load_weights(wpath).eval()
+    return net, blocks, net_info, params
+
+
+@pytest.fixture(scope="module")
+def yolov3_full(tmp_path_factory):
+    return build_full("yolov3", 416, tmp_path_factory)
+
+
+def alias_root(blocks, j):
+    """Block whose tensor block j's output IS (yolo passes its input through; a single-source
+    route is an alias) — mirrors the plan's resolution; -1 is the network input."""
+    while j >= 0:
+        b = blocks[j]
+        if b["type"] == "yolo":
+            j -= 1
+        elif b["type"] == "route" and len(b["layers"]) == 1:
+            j = b["layers"][0]
+        else:
+            break
+    return j
+
+
+def teacher_forced_network_check(net, blocks, params, B, size):
+    """Every conv op of the plan: read ITS input view from the device, run the oracle's conv block
+    (+ the fused shortcut / upsample) on it in fp32, compare with the op's output view."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(B, 3, size, size, generator=g)
+    net.forward(x.to(dev()))
+    eng = net.engine(B, size, size)
+    worst = (0.0, -1)
+    for i, b in enumerate(blocks):
+        if b["type"] != "convolutional":
+            continue
+        src = alias_root(blocks, i - 1)
+        xin = view_to_nchw(eng.views[src], B)
+        if src < 0:
+            xin = xin[:, :3]  # network input is stored padded to 16 channels
+        with torch.no_grad():
+            ref = DO.conv_block(xin, b, params[i])
+            nxt = blocks[i + 1] if i + 1 < len(blocks) else {"type": ""}
+            tgt = i
+            if nxt["type"] == "shortcut":
+                ref = ref + view_to_nchw(eng.views[alias_root(blocks, i + 1 + nxt["from"])], B)
+                tgt = i + 1
+            elif nxt["type"] == "upsample":
+                ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+                tgt = i + 1
+        got = view_to_nchw(eng.views[tgt], B)[:, :ref.shape[1]]
+        e = rel_err(got, ref)
+        if e > worst[0]:
+            worst = (e, i)
+        assert e <= CONV_TOL, (i, e)
+    return worst
+
+
+def test_yolov3_416_every_conv_teacher_forced(yolov3_full):
+    net, blocks, net_info, params = yolov3_full
+    worst = teacher_forced_network_check(net, blocks, params, 2, 416)
+    print(f"yolov3@416: worst teacher-forced conv error {worst[0]:.5f} at block {worst[1]} (75 convs)")
+
+
+def test_yolov3_416_tail_exact_and_candidates_nonempty(yolov3_full):
+    net, *_ = yolov3_full
+    rng = np.random.default_rng(1234)
+    imgs = [rng.integers(0, 256, (416, 416, 3), dtype=np.uint8) for _ in range(2)]
+    res = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, nms_iou_thresh=0.3, resize=False)
+    eng = net.engine(2, 416, 416)
+    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3)
+    equal, bad, tot = compare_detection_lists(res, want)
+    print(f"yolov3@416 tail: {equal}/2 images identical incl. order, {bad} of {tot} detections differ")
+    assert tot > 1000  # calibrated weights give thousands of candidates (F8)
+    assert bad <= max(4, 0.002 * tot)
+
+
+def test_batch_invariance_and_determinism(yolov3_full):
+    """Size-independent properties at the benchmark batch: an image's detections do not depend
+    on its position or batch size, and replays are bit-identical."""
+    net, *_ = yolov3_full
+    rng = np.random.default_rng(99)
+    imgs = [rng.integers(0, 256, (416, 416, 3), dtype=np.uint8) for _ in range(64)]
+    big = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, resize=False)
+    again = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, resize=False)
+    for a, b in zip(big, again):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    small = yolov3_b200.inference(net, [imgs[63], imgs[17]], device="cuda:0", prob_thresh=0.05, resize=False)
+    assert all(np.array_equal(x, y) for x, y in zip(small[0], big[63]))
+    assert all(np.array_equal(x, y) for x, y in zip(small[1], big[17]))
+
+
+def test_yolov3_spp_608_every_conv_teacher_forced(tmp_path_factory):
+    net, blocks, net_info, params = build_full("yolov3-spp", 608, tmp_path_factory)
+    worst = teacher_forced_network_check(net, blocks, params, 1, 608)
+    print(f"yolov3-spp@608: worst teacher-forced conv error {worst[0]:.5f} at block {worst[1]}")
+    # SPP block: the 2048-channel concat buffer equals pools of the bf16 tensor it was made from
+    eng = net.engine(1, 608, 608)
+    route = next(i for i, b in enumerate(blocks) if b["type"] == "route" and len(b["layers"]) == 4)
+    cat = view_to_nchw(eng.views[route], 1)
+    ident = cat[:, 1536:]
+    ref = torch.cat([DO.maxpool_block(ident, {"size": k, "stride": 1}) for k in (13, 9, 5)] + [ident], 1)
+    assert torch.equal(cat, ref)
+
+
+def test_yolov3_tiny_416_end_to_end(tmp_path_factory):
+    """Config 1 of BASELINE.json: tiny is shallow enough for an end-to-end comparison with the
+    fp32 oracle (reported; loose gate), plus the exact tail check."""
+    net, blocks, net_info, params = build_full("yolov3-tiny", 416, tmp_path_factory)
+    worst = teacher_forced_network_check(net, blocks, params, 1, 416)
+    print(f"yolov3-tiny@416: worst teacher-forced conv error {worst[0]:.5f} at block {worst[1]}")
+    rng = np.random.default_rng(1234)
+    imgs = [rng.integers(0, 256, (416, 416, 3), dtype=np.uint8)]
+    res = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, nms_iou_thresh=0.3, resize=False)
+    eng = net.engine(1, 416, 416)
+    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3)
+    equal, bad, tot = compare_detection_lists(res, want)
+    assert bad <= max(2, 0.002 * tot)
+    with torch.no_grad():
+        o = DO.forward(torch.from_numpy(PO.preprocess(imgs)), blocks, net_info, params)
+    full = PO.postprocess(o["bbox_xywh"].numpy(), o["class_prob"].numpy(), o["class_idx"].numpy(),
+                          [im.shape for im in imgs], 0.05, 0.3)
+    _, bad2, tot2 = compare_detection_lists(res, full)
+    print(f"yolov3-tiny@416 e2e vs fp32 oracle: {bad2} of {tot2} detections differ (bf16 vs fp32, reported)")

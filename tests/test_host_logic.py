@@ -1,0 +1,187 @@
+"""CPU: host-side logic of the package (parser, module tree, weight loader, execution plan,
+result ordering), the C-ABI library's exports, and the no-fallback guarantees."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import yolov3_b200
+from yolov3_b200 import _lib
+from yolov3_b200.engine import Engine
+from yolov3_b200.inference import _order_like_reference, _set_order
+from conftest import GOLDEN, MODELS, PKG, ROOT
+
+
+def test_parse_config_and_cache_set_match_reference():
+    g = json.load(open(os.path.join(GOLDEN, "parse_config.json")))
+    for name, path in (("yolov3", f"{MODELS}/yolov3.cfg"), ("yolov3-tiny", f"{MODELS}/yolov3-tiny.cfg"),
+                       ("yolov3-spp", f"{MODELS}/yolov3-spp.cfg"), ("micro", f"{GOLDEN}/micro.cfg")):
+        net = yolov3_b200.Darknet(path, device="cuda")
+        assert net.blocks == g[name]["blocks"]
+        assert net.net_info == g[name]["net_info"]
+        assert sorted(net.blocks_to_cache) == g[name]["blocks_to_cache"]
+
+
+def test_parse_config_quirks(tmp_path):
+    cfg = tmp_path / "q.cfg"
+    cfg.write_text("[net]\nwidth=32\n# comment\n  \nheight=32\nchannels=3\nsteps=1,2\n\n[convolutional]\nfilters=16\n"
+                   "size=3\nstride=1\npad=1\nactivation=linear\n[route]\nlayers=-1\n[yolo]\nmask=0\n"
+                   "anchors=1,2, 3,4\nclasses=1\nscale=.5\n")
+    blocks, net_info = yolov3_b200.parse_config(str(cfg))
+    assert net_info == {"type": "net", "width": 32, "height": 32, "channels": 3, "steps": [1, 2]}
+    assert blocks[1]["layers"] == [-1]            # scalar route -> list
+    assert blocks[2]["mask"] == 0                 # single value stays scalar
+    assert blocks[2]["anchors"] == [[1, 2], [3, 4]]
+    assert blocks[2]["scale"] == 0.5 and blocks[0]["activation"] == "linear"
+
+
+def test_module_tree_names_and_state_dict():
+    net = yolov3_b200.Darknet(f"{MODELS}/yolov3-tiny.cfg", device="cuda")
+    assert isinstance(net, torch.nn.Module) and len(net.modules_) == 24
+    names = [n for n, _ in net.modules_[0].named_children()]
+    assert names == ["conv_0", "batch_norm_0", "leaky_0"]
+    assert [n for n, _ in net.modules_[15].named_children()] == ["conv_15"]  # linear head: no activation module
+    assert net.modules_[15][0].bias is not None and net.modules_[0][0].bias is None
+    assert [n for n, _ in net.modules_[11].named_children()] == ["maxpool_11"]
+    assert "modules_.0.conv_0.weight" in net.state_dict()
+    n_float = sum(p.numel() for p in net.parameters()) + sum(
+        b.numel() for n, b in net.named_buffers() if "running" in n)
+    assert n_float == 8858734  # yolov3-tiny.weights payload
+
+
+def test_load_weights_fills_parameters_and_validates_length(tmp_path):
+    net = yolov3_b200.Darknet(f"{GOLDEN}/micro.cfg", device="cuda")
+    assert net.load_weights(f"{GOLDEN}/micro.weights") is net
+    assert net.header.tolist() == [0, 2, 0, 0, 0]
+    raw = np.fromfile(f"{GOLDEN}/micro.weights", dtype=np.float32)[5:]
+    bn = net.modules_[0][1]
+    assert np.array_equal(bn.bias.detach().numpy(), raw[:16])
+    assert np.array_equal(bn.weight.detach().numpy(), raw[16:32])
+    assert np.array_equal(bn.running_mean.numpy(), raw[32:48])
+    assert np.array_equal(bn.running_var.numpy(), raw[48:64])
+    assert np.array_equal(net.modules_[0][0].weight.detach().numpy().ravel(), raw[64:64 + 16 * 3 * 9])
+    data = open(f"{GOLDEN}/micro.weights", "rb").read()
+    short = tmp_path / "short.weights"
+    short.write_bytes(data[: len(data) - 400])
+    with pytest.raises(RuntimeError):
+        yolov3_b200.Darknet(f"{GOLDEN}/micro.cfg", device="cuda").load_weights(str(short))
+    longer = tmp_path / "long.weights"
+    longer.write_bytes(data + b"\0" * 64)  # trailing values are ignored, as in the reference
+    yolov3_b200.Darknet(f"{GOLDEN}/micro.cfg", device="cuda").load_weights(str(longer))
+
+
+@pytest.mark.parametrize("name,size,convs,shortcuts,upsamples,M,gflop", [
+    ("yolov3", 416, 75, 23, 2, 10647, 65.864), ("yolov3-tiny", 416, 13, 0, 1, 2535, 5.565),
+    ("yolov3-spp", 608, 76, 23, 2, 22743, 141.449)])
+def test_execution_plan_fuses_everything(name, size, convs, shortcuts, upsamples, M, gflop):
+    net = yolov3_b200.Darknet(f"{MODELS}/{name}.cfg", device="cuda")
+    eng = Engine(net, 2, size, size, torch.device("meta"))
+    kinds = [re.sub(r"[\d_]+$", "", n) for n in eng.op_names]
+    assert kinds.count("conv") == convs
+    assert "add" not in kinds and "upsample" not in kinds and "copy" not in kinds  # all fused / zero-copy
+    assert eng.num_fused["shortcut"] == shortcuts and eng.num_fused["upsample"] == upsamples
+    assert eng.M == M and eng.num_classes == 80
+    assert abs(eng.conv_flops / 2 / 1e9 - gflop) < 1e-3  # algorithmic FLOPs of SURVEY.md §8d
+    if name == "yolov3-spp":
+        assert kinds.count("spp") == 1 and "maxpool" not in kinds
+
+
+def test_plan_falls_back_to_standalone_kernels_when_intermediate_is_shared(tmp_path):
+    # the conv feeding the shortcut is ALSO routed: the add cannot be fused into its epilogue
+    cfg = tmp_path / "shared.cfg"
+    cfg.write_text(
+        "[net]\nwidth=32\nheight=32\nchannels=3\n"
+        "[convolutional]\nbatch_normalize=1\nfilters=16\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+        "[convolutional]\nbatch_normalize=1\nfilters=16\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+        "[shortcut]\nfrom=-2\nactivation=linear\n"
+        "[route]\nlayers=-2,-1\n"
+        "[upsample]\nstride=2\n"
+        "[convolutional]\nfilters=18\nsize=1\nstride=1\npad=1\nactivation=linear\n"
+        "[yolo]\nmask=0,1,2\nanchors=1,2, 3,4, 5,6\nclasses=1\n")
+    net = yolov3_b200.Darknet(str(cfg), device="cuda")
+    eng = Engine(net, 1, 32, 32, torch.device("meta"))
+    kinds = [re.sub(r"[\d_]+$", "", n) for n in eng.op_names]
+    assert "add" in kinds and "upsample" in kinds
+    assert eng.num_fused["shortcut"] == 0
+
+
+def test_unsupported_cfg_raises_instead_of_falling_back(tmp_path):
+    cfg = tmp_path / "bad.cfg"
+    cfg.write_text("[net]\nwidth=32\nheight=32\nchannels=3\n[convolutional]\nfilters=16\nsize=5\nstride=1\npad=1\n"
+                   "activation=leaky\n[yolo]\nmask=0,1\nanchors=1,2, 3,4\nclasses=3\n")
+    net = yolov3_b200.Darknet(str(cfg), device="cuda")
+    with pytest.raises(NotImplementedError):
+        Engine(net, 1, 32, 32, torch.device("meta"))
+
+
+def test_cxywh_to_tlbr_known_answer():
+    # tests/test_inference.py:12-23 of the reference
+    z = np.load(os.path.join(GOLDEN, "nms.npz"))
+    assert np.array_equal(yolov3_b200.cxywh_to_tlbr(z["kat_in"]), z["kat_out"])
+
+
+def test_reference_class_visiting_order_is_reproduced():
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n = int(rng.integers(1, 400))
+        classes = int(rng.choice([1, 2, 5, 9, 33, 80, 257, 1000]))
+        cls = rng.integers(0, classes, n).astype(np.int64)
+        first = np.full(max(classes, 1), np.iinfo(np.int32).max, dtype=np.int32)
+        for pos, c in enumerate(cls):
+            first[c] = min(first[c], pos)
+        assert _set_order(first) == list(set(cls))  # the reference's loop order (inference.py:247-250)
+        # full permutation: records sorted (class asc, prob desc) -> reference order
+        prob = rng.permutation(n).astype(np.float32)
+        order = np.lexsort((-prob, cls))
+        perm = _order_like_reference(cls[order], first)
+        want = []
+        for c in set(cls):
+            members = np.where(cls == c)[0]
+            want.extend(members[np.argsort(prob[members])[::-1]].tolist())
+        assert order[perm].tolist() == want
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "yolov3_b200.h")).read()
+    declared = set(re.findall(r"\b(y3_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.y3_abi_version() == 1
+    lib.y3_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.y3_last_error(), bytes)
+
+
+def test_no_cpu_fallback():
+    net = yolov3_b200.Darknet(f"{GOLDEN}/micro.cfg", device="cpu").load_weights(f"{GOLDEN}/micro.weights")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU"):
+            net.forward(torch.rand(1, 3, 64, 64))
+        with pytest.raises(RuntimeError):
+            yolov3_b200.inference(net, np.zeros((64, 64, 3), np.uint8), device="cuda")
+        with pytest.raises(RuntimeError):
+            yolov3_b200.non_max_suppression(np.zeros((2, 4), np.int64), np.ones(2, np.float32))
+    with pytest.raises(RuntimeError):
+        _lib.maxpool(0, 0, 1, 1, 1, 8, 8, 8, 2, 2) if torch.cuda.is_available() else _lib.require_device("cpu")
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or the C sources may touch it."""
+    bad = []
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|nms_oracle", text, re.M):
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
+    # bench.py / __graft_entry__.py may use it only in the sanctioned places
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    for m in re.finditer(r"^.*\boracle\b.*$", bench, re.M):
+        line = m.group(0)
+        assert "cpu_baseline" in line or "reference" in line or line.lstrip().startswith(("#", '"', "from oracle", "import oracle")), line

@@ -1,0 +1,76 @@
+"""CPU, world_size 2, gloo: the N>1 path's host logic — batch sharding and the detection gather
+(the only collective of the hot path)."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _synth_results(rng, n_img):
+    out = []
+    for _ in range(n_img):
+        k = int(rng.integers(0, 40))
+        tlbr = rng.integers(-50, 700, (k, 4)).astype(np.int64)
+        prob = rng.random(k, dtype=np.float32)
+        cls = rng.integers(0, 80, k).astype(np.int64)
+        out.append([tlbr, prob, cls])
+    return out
+
+
+def _worker(rank, world, port, total_images, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from yolov3_b200 import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = D.shard_range(total_images, rank, world)
+        everything = _synth_results(np.random.default_rng(5), total_images)  # same on every rank
+        rec, counts = D.pack_results(everything[lo:hi])
+        all_rec, all_counts = D.gather_detections(rec, counts, device="cpu")
+        got = D.unpack_results(all_rec, all_counts)
+        ok = len(got) == total_images
+        for a, b in zip(got, everything):
+            ok = ok and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
+        q.put((rank, bool(ok), lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(total_images, port):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_images, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_gather_detections_world2_even_split():
+    res = _run(8, 29611)
+    assert [r[1] for r in res] == [True, True]
+    assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 4, 4, 8)
+
+
+def test_gather_detections_world2_ragged_split():
+    res = _run(5, 29612)  # ranks own 3 and 2 images
+    assert [r[1] for r in res] == [True, True]
+    assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 3, 3, 5)
+
+
+def test_shard_range_covers_batch():
+    from yolov3_b200.distributed import shard_range
+    for n in (1, 7, 64, 65):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
