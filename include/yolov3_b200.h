@@ -78,8 +78,10 @@ typedef struct y3_conv_desc {
   int32_t leaky;            /* 1: LeakyReLU(0.1); 0: linear (identity)  */
   int32_t out_f32;          /* 1: y is float32; 0: bf16                 */
   int32_t upsample2x;       /* 1: fused nearest x2 store                */
-  int32_t flags;            /* bit0: load A through the im2col tensor map
-                               even for 1x1/s1 (validation knob); else 0 */
+  int32_t flags;            /* validation knobs, normally 0.  bit0: load A
+                               through the im2col tensor map even for 1x1/s1;
+                               bit1: use the direct (register->global)
+                               epilogue instead of the staged TMA-store one */
 } y3_conv_desc;
 
 int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w,

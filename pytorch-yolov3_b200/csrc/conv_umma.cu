@@ -15,13 +15,18 @@
 //             of two TMEM accumulator buffers; tcgen05.commit releases smem stages and
 //             publishes the finished accumulator.
 //   warps2-5: epilogue.  tcgen05.ld the accumulator (lane = output pixel), + folded-BN bias,
-//             LeakyReLU, + residual, convert, store NHWC (optionally to the 2x2 upsampled
-//             block, optionally into a channel slice of a concat buffer via ld_y).
+//             LeakyReLU, + residual, convert to bf16.  STAGED form (the common one): each warp
+//             owns a swizzled smem staging slab for its 32 rows; the shortcut operand is
+//             TMA-loaded into the slab while the MMAs run, the result overwrites it in place and
+//             leaves through TMA stores (full-line writes, M tail clipped by the tensor map,
+//             ld_y pitch = channel slice of a concat buffer).  DIRECT form (float32 head
+//             logits, fused 2x upsample): registers -> st.global, one row per thread.
 // The double-buffered accumulator lets tile i's epilogue overlap tile i+1's MMAs.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <cuda.h>  // CUtensorMap + enums only; entry points are fetched at run time
+#include <string.h>
 
 namespace y3 {
 
@@ -46,7 +51,7 @@ struct ConvKernelParams {
   int leaky, out_f32, upsample;
 };
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool STAGED>
 struct ConvCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -54,12 +59,19 @@ struct ConvCfg {
   static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_STRIDE + B_STRIDE;
-  static constexpr int STAGES_RAW = 196608 / STAGE_BYTES;
+  // epilogue staging: 128 rows x BLOCK_N bf16, in column blocks of one swizzle span each
+  static constexpr int EPI_SPAN = BLOCK_N * 2 >= 128 ? 128 : BLOCK_N * 2;  // bytes per staged row
+  static constexpr int EPI_COLS = EPI_SPAN / 2;                            // columns per block
+  static constexpr int EPI_BLOCKS = BLOCK_N / EPI_COLS;
+  static constexpr int EPI_BLOCK_BYTES = BLOCK_M * EPI_SPAN;
+  static constexpr int STAGING_BYTES = STAGED ? BLOCK_M * BLOCK_N * 2 : 0;
+  static constexpr int SMEM_LIMIT = 232448 - 1024 /*align slack*/ - 256 /*barriers*/;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS_RAW = 2 * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
                                  : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
   // UMMA smem descriptor pieces (K-major, swizzle span = BLOCK_K*2 bytes)
   static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
   static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
@@ -73,22 +85,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t 
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024B-aligned
+  const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
+  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], res[4], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int q) { return bar_base + 8u * (2 * STAGES + 4 + q); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 8);
   uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -98,6 +113,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
+    if (STAGED) {
+      ptx::prefetch_tensormap(&tmap_y);
+      if (p.res) ptx::prefetch_tensormap(&tmap_r);
+    }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
@@ -106,6 +125,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
     }
+    for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -195,50 +215,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int m = m_tile * BLOCK_M + row;
+      const int m0 = m_tile * BLOCK_M;
+      const int m = m0 + row;
       const int n0 = n_tile * BLOCK_N;
-      const bool valid = m < p.M;
-
-      // destination pixel index(es)
-      long long dst_pix = m;
-      int up_w2 = 0;
-      if (p.upsample) {
-        const int img = m / p.HoWo;
-        const int rem = m - img * p.HoWo;
-        const int ho = rem / p.Wo;
-        const int wo = rem - ho * p.Wo;
-        up_w2 = 2 * p.Wo;
-        dst_pix = ((long long)img * (2 * p.Ho) + 2 * ho) * up_w2 + 2 * wo;
-      }
-      const __nv_bfloat16* res_row = p.res ? p.res + (long long)m * p.ld_res + n0 : nullptr;
-
-      ptx::mbar_wait(tfull_bar(acc), acc_phase);
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
 
+      if constexpr (STAGED) {
+        // ---- staged: smem slab (swizzled like the TMA box) -> TMA store ----
+        // slab row r of column block cb lives at staging + cb*EPI_BLOCK_BYTES + r*EPI_SPAN; its
+        // 16-byte units are XOR-swizzled exactly as CU_TENSOR_MAP_SWIZZLE_{128,64,32}B does.
+        constexpr int SPAN = Cfg::EPI_SPAN;
+        const uint32_t swz = SPAN == 128 ? (row & 7) : SPAN == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);
+        const uint32_t row_base = staging_base + row * SPAN;
+        const uint32_t warp_base = staging_base + quarter * 32 * SPAN;
+        const bool has_res = p.res != nullptr;
+        if (lane == 0) {
+          // the previous tile's TMA stores must have finished READING the slab before it is reused
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (has_res) {
+            ptx::mbar_arrive_expect_tx(res_bar(quarter), 32 * BLOCK_N * 2);
+#pragma unroll
+            for (int cb = 0; cb < Cfg::EPI_BLOCKS; ++cb)
+              ptx::tma_load_2d(warp_base + cb * Cfg::EPI_BLOCK_BYTES, &tmap_r, res_bar(quarter),
+                               n0 + cb * Cfg::EPI_COLS, m0 + quarter * 32);
+          }
+        }
+        __syncwarp();
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        if (has_res) ptx::mbar_wait(res_bar(quarter), it & 1);
+
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        float f[16];
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          float f[16];
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b = __ldg(bias4 + q);
-          f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-          f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-          f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
-        }
-        if (p.leaky) {
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(bias4 + q);
+            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+          }
+          if (p.leaky) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-        }
-        if (valid) {
-          if (res_row) {
-            const uint4 r0 = ld_nc_16(res_row + c0);
-            const uint4 r1 = ld_nc_16(res_row + c0 + 8);
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+          }
+          const int cb = c0 / Cfg::EPI_COLS;
+          const uint32_t u0 = uint32_t((c0 % Cfg::EPI_COLS) >> 3);  // 16-byte unit index in the row
+          const uint32_t a0 = row_base + cb * Cfg::EPI_BLOCK_BYTES + ((u0 ^ swz) << 4);
+          const uint32_t a1 = row_base + cb * Cfg::EPI_BLOCK_BYTES + (((u0 + 1) ^ swz) << 4);
+          if (has_res) {
+            uint4 r0, r1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -247,36 +280,105 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               f[2 * j + 1] += t.y;
             }
           }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + dst_pix * p.ld_out + n0 + c0;
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pack_bf16x2(f[0], f[1])),
+                       "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pack_bf16x2(f[8], f[9])),
+                       "r"(pack_bf16x2(f[10], f[11])), "r"(pack_bf16x2(f[12], f[13])), "r"(pack_bf16x2(f[14], f[15])) : "memory");
+        }
+        // TMEM reads done: hand the accumulator back; publish the slab to the async proxy; store
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(tempty_bar(acc));
+          if (m0 + quarter * 32 < p.M) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              st_16(o + 4 * q, make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
-                                          __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
-          } else {
-            const uint4 o0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            const uint4 o1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                                        pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dst_pix * p.ld_out + n0 + c0;
-            st_16(o, o0);
-            st_16(o + 8, o1);
-            if (p.upsample) {
-              __nv_bfloat16* o01 = o + p.ld_out;
-              __nv_bfloat16* o10 = o + (long long)up_w2 * p.ld_out;
-              __nv_bfloat16* o11 = o10 + p.ld_out;
-              st_16(o01, o0); st_16(o01 + 8, o1);
-              st_16(o10, o0); st_16(o10 + 8, o1);
-              st_16(o11, o0); st_16(o11 + 8, o1);
+            for (int cb = 0; cb < Cfg::EPI_BLOCKS; ++cb)
+              ptx::tma_store_2d(&tmap_y, warp_base + cb * Cfg::EPI_BLOCK_BYTES, n0 + cb * Cfg::EPI_COLS,
+                                m0 + quarter * 32);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        // ---- direct: registers -> global, one output row per thread ----
+        const bool valid = m < p.M;
+        long long dst_pix = m;
+        int up_w2 = 0;
+        if (p.upsample) {
+          const int img = m / p.HoWo;
+          const int rem = m - img * p.HoWo;
+          const int ho = rem / p.Wo;
+          const int wo = rem - ho * p.Wo;
+          up_w2 = 2 * p.Wo;
+          dst_pix = ((long long)img * (2 * p.Ho) + 2 * ho) * up_w2 + 2 * wo;
+        }
+        const __nv_bfloat16* res_row = p.res ? p.res + (long long)m * p.ld_res + n0 : nullptr;
+
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          float f[16];
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = __ldg(bias4 + q);
+            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+          }
+          if (p.leaky) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
+          }
+          if (valid) {
+            if (res_row) {
+              const uint4 r0 = ld_nc_16(res_row + c0);
+              const uint4 r1 = ld_nc_16(res_row + c0 + 8);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 t = unpack_bf16x2(rr[j]);
+                f[2 * j] += t.x;
+                f[2 * j + 1] += t.y;
+              }
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + dst_pix * p.ld_out + n0 + c0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                st_16(o + 4 * q, make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                                            __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3])));
+            } else {
+              const uint4 o0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                          pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              const uint4 o1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                          pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dst_pix * p.ld_out + n0 + c0;
+              st_16(o, o0);
+              st_16(o + 8, o1);
+              if (p.upsample) {
+                __nv_bfloat16* o01 = o + p.ld_out;
+                __nv_bfloat16* o10 = o + (long long)up_w2 * p.ld_out;
+                __nv_bfloat16* o11 = o10 + p.ld_out;
+                st_16(o01, o0); st_16(o01 + 8, o1);
+                st_16(o10, o0); st_16(o10 + 8, o1);
+                st_16(o11, o0); st_16(o11 + 8, o1);
+              }
             }
           }
         }
+        // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       }
-      // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
     }
+    if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   ptx::tc_fence_before();
@@ -376,10 +478,10 @@ static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x,
   return Y3_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool STAGED>
 static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, cudaStream_t stream, int force_im2col) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED>;
   const int ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
   const long long M = (long long)d->n * ho * wo;
@@ -404,7 +506,9 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   int rc = resolve_driver_entry_points();
   if (rc != Y3_OK) return rc;
 
-  alignas(64) CUtensorMap tmap_a, tmap_b;
+  alignas(64) CUtensorMap tmap_a, tmap_b, tmap_y, tmap_r;
+  memset(&tmap_y, 0, sizeof(tmap_y));
+  memset(&tmap_r, 0, sizeof(tmap_r));
   if (p.a_tiled) {
     rc = encode_2d(&tmap_a, x, (uint64_t)d->cin, (uint64_t)d->n * d->h * d->w, (uint64_t)d->ld_x * 2,
                    BLOCK_K, BLOCK_M, BLOCK_K);
@@ -416,7 +520,19 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   rc = encode_2d(&tmap_b, w, k_total, (uint64_t)d->cout, k_total * 2, BLOCK_K, BLOCK_N, BLOCK_K);
   if (rc != Y3_OK) return rc;
 
-  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K>;
+  if (STAGED) {
+    // output / residual tiles: [32 rows x EPI_COLS] boxes, swizzle span = EPI_SPAN bytes
+    const int span_k = Cfg::EPI_SPAN / 2;  // "block_k" equivalent that selects the same swizzle mode
+    rc = encode_2d(&tmap_y, y, (uint64_t)d->cout, (uint64_t)M, (uint64_t)d->ld_y * 2, Cfg::EPI_COLS, 32, span_k);
+    if (rc != Y3_OK) return rc;
+    if (residual) {
+      rc = encode_2d(&tmap_r, residual, (uint64_t)d->cout, (uint64_t)M, (uint64_t)d->ld_res * 2, Cfg::EPI_COLS, 32,
+                     span_k);
+      if (rc != Y3_OK) return rc;
+    }
+  }
+
+  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     Y3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -424,20 +540,29 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kernel<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmap_a, tmap_b, p);
+  kernel<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmap_a, tmap_b, tmap_y, tmap_r, p);
   Y3_LAUNCH_OK("conv_umma_kernel");
   return Y3_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+static int dispatch_epi(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                        const void* residual, void* y, cudaStream_t stream, int force_im2col) {
+  // float32 head logits and the fused 2x upsample use the direct (register -> global) epilogue
+  if (d->out_f32 || d->upsample2x || (d->flags & 2))
+    return launch_conv<BLOCK_N, BLOCK_K, false>(d, x, w, bias, residual, y, stream, force_im2col);
+  return launch_conv<BLOCK_N, BLOCK_K, true>(d, x, w, bias, residual, y, stream, force_im2col);
 }
 
 template <int BLOCK_K>
 static int dispatch_n(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                       const void* residual, void* y, cudaStream_t stream, int force_im2col) {
   const int c = d->cout;
-  if (c % 256 == 0) return launch_conv<256, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
-  if (c % 128 == 0) return launch_conv<128, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
-  if (c % 64 == 0) return launch_conv<64, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
-  if (c % 32 == 0) return launch_conv<32, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
-  return launch_conv<16, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 256 == 0) return dispatch_epi<256, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 128 == 0) return dispatch_epi<128, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 64 == 0) return dispatch_epi<64, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  if (c % 32 == 0) return dispatch_epi<32, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
+  return dispatch_epi<16, BLOCK_K>(d, x, w, bias, residual, y, stream, force_im2col);
 }
 
 static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, const float* bias,

@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-D tiled store: smem box -> global (bulk async group; rows/cols outside the tensor are clipped).
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 // 4-D im2col load over an NHWC tensor: (c, w, h, n) is the first base pixel in
 // INPUT coordinates (output pixel * stride - pad), (off_w, off_h) the filter tap.
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const void* tmap,

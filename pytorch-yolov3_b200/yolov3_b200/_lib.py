@@ -78,9 +78,6 @@ def lib():
     L.y3_nms.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_size_t, c_void_p]
     L.y3_compact_kept.argtypes = [c_void_p] * 3 + [c_int32] * 2 + [c_void_p] * 2 + [c_int32, c_void_p]
-    for name in EXPORTS:
-        if getattr(L, name).restype is ctypes.c_int and name not in ("y3_abi_version",):
-            pass  # int status is ctypes' default restype
     if L.y3_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libyolov3_b200.so ABI {L.y3_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L
@@ -133,10 +130,10 @@ def reset_launch_count():
 # ---- kernels --------------------------------------------------------------------------------
 
 def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, leaky,
-           res_ptr=None, ld_res=0, out_f32=False, upsample2x=False, force_im2col=False):
+           res_ptr=None, ld_res=0, out_f32=False, upsample2x=False, force_im2col=False, force_direct=False):
     """Raw-pointer form used by the engine plan (views into concat buffers are plain pointers)."""
     d = ConvDesc(n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, ld_res, int(leaky), int(out_f32),
-                 int(upsample2x), 1 if force_im2col else 0)
+                 int(upsample2x), (1 if force_im2col else 0) | (2 if force_direct else 0))
     _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
 
 

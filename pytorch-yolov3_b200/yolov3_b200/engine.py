@@ -464,21 +464,31 @@ class Engine:
             self.launch((kind, float(prob_thresh), float(iou_thresh)))
         return self.dets, self.det_counts, self.first_box
 
-    def time_convs(self, iters=3):
-        """CUDA-event time of every convolution launch run eagerly (for bench.py's roofline
-        block): returns (total seconds per forward, [(block, seconds, flops)])."""
+    def time_convs(self, iters=10):
+        """Device time of every convolution launch, each timed ALONE: the launch is captured
+        `iters` times into a small CUDA graph (so host launch latency does not pace the
+        measurement) and the replay is bracketed by CUDA events on the same stream.
+        Returns (seconds per forward summed over convs, [(block, seconds, flops)])."""
         with torch.cuda.device(self.device):
             per = []
-            for blk, fn, flops in self.conv_ops:
-                fn()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(iters):
+            stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(stream):
+                for blk, fn, flops in self.conv_ops:
                     fn()
-                e1.record()
-                torch.cuda.synchronize()
-                per.append((blk, e0.elapsed_time(e1) * 1e-3 / iters, flops))
+                    stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        for _ in range(iters):
+                            fn()
+                    g.replay()
+                    stream.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    g.replay()
+                    e1.record(stream)
+                    stream.synchronize()
+                    per.append((blk, e0.elapsed_time(e1) * 1e-3 / iters, flops))
+                    del g
             return sum(p[1] for p in per), per
 
 

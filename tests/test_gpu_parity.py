@@ -344,13 +344,40 @@ def compare_detection_lists(got, want):
     equal, bad, tot = 0, 0, 0
     for g, w in zip(got, want):
         tot += len(w[1])
-        if all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(g, w)):
+        # same boxes and classes in the same ORDER; probabilities may differ in the last ulp
+        # (device expf vs torch's vectorised exp on the same logits)
+        if (g[0].shape == w[0].shape and np.array_equal(g[0], w[0]) and np.array_equal(g[2], w[2])
+                and np.allclose(g[1], w[1], rtol=2e-6, atol=0) and all(a.dtype == b.dtype for a, b in zip(g, w))):
             equal += 1
             continue
         gs = {tuple(t) + (int(c),) for t, c in zip(g[0].tolist(), g[2])}
         ws = {tuple(t) + (int(c),) for t, c in zip(w[0].tolist(), w[2])}
         bad += len(gs ^ ws)
     return equal, bad, tot
+
+
+def match_rate(got, want, iou_thr):
+    """How many reference detections have a same-class detection of ours with IoU >= iou_thr
+    ("+1" pixel convention, one-to-one greedy by IoU)."""
+    matched = total = 0
+    for g, w in zip(got, want):
+        total += len(w[1])
+        used = np.zeros(len(g[1]), bool)
+        for box, cls in zip(w[0], w[2]):
+            cand = np.nonzero((g[2] == cls) & ~used)[0]
+            if cand.size == 0:
+                continue
+            b = g[0][cand]
+            iw = np.clip(np.minimum(b[:, 2], box[2]) - np.maximum(b[:, 0], box[0]) + 1, 0, None)
+            ih = np.clip(np.minimum(b[:, 3], box[3]) - np.maximum(b[:, 1], box[1]) + 1, 0, None)
+            inter = iw * ih
+            area = (b[:, 2] - b[:, 0] + 1) * (b[:, 3] - b[:, 1] + 1)
+            iou = inter / (area + (box[2] - box[0] + 1) * (box[3] - box[1] + 1) - inter)
+            j = int(np.argmax(iou))
+            if iou[j] >= iou_thr:
+                matched += 1
+                used[cand[j]] = True
+    return matched, total
 
 
 def test_micro_inference_tail_is_exact_on_identical_logits(micro):
@@ -366,11 +393,14 @@ def test_micro_inference_tail_is_exact_on_identical_logits(micro):
     equal, bad, tot = compare_detection_lists(res, want)
     print(f"micro tail: {equal}/2 images identical incl. order, {bad} of {tot} detections differ")
     assert bad <= max(2, 0.002 * tot)
-    # and against the reference's end-to-end golden (fp32 everywhere): report + loose gate
+    # and against the reference's end-to-end golden (fp32 everywhere).  bf16 activations move box
+    # edges by a pixel on these 64-px images, so this is matched by class + IoU and REPORTED;
+    # the gates are the teacher-forced conv bound and the exact tail above.
     gold = [[z[f"img{i}_tlbr"], z[f"img{i}_prob"], z[f"img{i}_cls"]] for i in range(2)]
-    _, bad2, tot2 = compare_detection_lists(res, gold)
-    print(f"micro e2e vs fp32 reference golden: {bad2} of {tot2} detections differ")
-    assert bad2 <= 0.25 * tot2
+    for thr in (0.99, 0.5):
+        m, t = match_rate(res, gold, thr)
+        print(f"micro e2e vs fp32 reference golden: {m}/{t} reference detections matched at IoU>={thr}, same class")
+    assert m >= 0.6 * t
 
 
 def test_inference_argument_semantics(micro):
@@ -470,6 +500,7 @@ def test_yolov3_416_tail_exact_and_candidates_nonempty(yolov3_full):
     print(f"yolov3@416 tail: {equal}/2 images identical incl. order, {bad} of {tot} detections differ")
     assert tot > 1000  # calibrated weights give thousands of candidates (F8)
     assert bad <= max(4, 0.002 * tot)
+    assert equal == 2 or bad > 0  # identical sets must also come back in the reference's order
 
 
 def test_batch_invariance_and_determinism(yolov3_full):
@@ -517,5 +548,6 @@ def test_yolov3_tiny_416_end_to_end(tmp_path_factory):
         o = DO.forward(torch.from_numpy(PO.preprocess(imgs)), blocks, net_info, params)
     full = PO.postprocess(o["bbox_xywh"].numpy(), o["class_prob"].numpy(), o["class_idx"].numpy(),
                           [im.shape for im in imgs], 0.05, 0.3)
-    _, bad2, tot2 = compare_detection_lists(res, full)
-    print(f"yolov3-tiny@416 e2e vs fp32 oracle: {bad2} of {tot2} detections differ (bf16 vs fp32, reported)")
+    for thr in (0.99, 0.5):
+        m, t = match_rate(res, full, thr)
+        print(f"yolov3-tiny@416 e2e vs fp32 oracle: {m}/{t} detections matched at IoU>={thr}, same class (reported)")

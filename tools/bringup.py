@@ -62,18 +62,26 @@ def run_conv_case(case):
     w_krsc = wt.permute(0, 2, 3, 1).contiguous()
     r_nhwc = r.permute(0, 2, 3, 1).contiguous() if res else None
     oh, ow = (2 * ho, 2 * wo) if up else (ho, wo)
-    y = torch.full((n, oh, ow, cout), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    t0 = time.time()
-    _lib.conv2d(x_nhwc.data_ptr(), w_krsc, bias, y.data_ptr(), n=n, h=h, w_in=w, cin=cin, cout=cout, ksize=k,
-                stride=s, pad=pad, ld_x=cin, ld_y=cout, leaky=leaky, res_ptr=r_nhwc.data_ptr() if res else None,
-                ld_res=cout, out_f32=bool(f32), upsample2x=bool(up), force_im2col=bool(force))
-    torch.cuda.synchronize()
-    dt = time.time() - t0
-    got = y.float().permute(0, 3, 1, 2)
-    err = (got - ref).abs().max().item() / ref.abs().max().item()
-    nan = int(torch.isnan(got).sum().item())
-    ok = nan == 0 and err < 1e-2
-    out = {"case": name, "ok": ok, "rel_err": err, "nan": nan, "ms_first_call": dt * 1e3}
+    out = None
+    for direct in (False, True):
+        y = torch.full((n, oh, ow, cout), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        t0 = time.time()
+        _lib.conv2d(x_nhwc.data_ptr(), w_krsc, bias, y.data_ptr(), n=n, h=h, w_in=w, cin=cin, cout=cout, ksize=k,
+                    stride=s, pad=pad, ld_x=cin, ld_y=cout, leaky=leaky, res_ptr=r_nhwc.data_ptr() if res else None,
+                    ld_res=cout, out_f32=bool(f32), upsample2x=bool(up), force_im2col=bool(force),
+                    force_direct=direct)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        got = y.float().permute(0, 3, 1, 2)
+        err = (got - ref).abs().max().item() / ref.abs().max().item()
+        nan = int(torch.isnan(got).sum().item())
+        ok = nan == 0 and err < 1e-2
+        cur = {"case": name + ("/direct" if direct else "/staged"), "ok": ok, "rel_err": err, "nan": nan,
+               "ms_first_call": dt * 1e3}
+        if out is None or not ok:
+            out = cur
+        if not ok:
+            break
     if not ok:  # locate the damage
         d = (got - ref).abs()
         bad = (d > 1e-2 * ref.abs().max()) | torch.isnan(got)
