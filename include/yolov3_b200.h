@@ -127,6 +127,15 @@ int y3_pack_nchw_f32(const float* x, void* y, int32_t n, int32_t c, int32_t h,
 int y3_pack_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h, int32_t w,
                    int32_t c_pad, void* stream);
 
+/* Same two conversions fused with the im2col of a FIRST layer that is a 3x3 /
+ * stride 1 / pad 1 convolution over c <= 3 channels: y is [N*H*W, k_pad] bf16,
+ * row = the 9*c taps in (r, s, c) order (the weight layout) then zeros.  The
+ * first convolution then runs as y3_conv2d with ksize 1, cin = k_pad. */
+int y3_im2col3x3_nchw_f32(const float* x, void* y, int32_t n, int32_t c,
+                          int32_t h, int32_t w, int32_t k_pad, void* stream);
+int y3_im2col3x3_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h,
+                        int32_t w, int32_t k_pad, void* stream);
+
 /* ---- a10/a11/a13/a14: YOLO decode ----------------------------------------- */
 /*
  * One YOLO head.  logits: float32 NHWC [N,g_h,g_w,ld] with channel

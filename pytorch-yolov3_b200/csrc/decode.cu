@@ -67,6 +67,11 @@ __device__ __forceinline__ BoxOut decode_box(const y3_head_desc& d, const float*
   return o;
 }
 
+__device__ __forceinline__ int f2i_trunc(float v) {
+  // numpy astype(int) truncates toward zero; values stay far inside int32 for any sane logit
+  return __float2int_rz(v);
+}
+
 __device__ __forceinline__ bool next_box(const y3_head_desc& d, long long wid, int& img, int& a,
                                          int& row, int& col, int& m) {
   const int cells = d.g_h * d.g_w;
@@ -99,40 +104,55 @@ decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
   }
 }
 
-__device__ __forceinline__ int f2i_trunc(float v) {
-  // numpy astype(int) truncates toward zero; values stay far inside int32 for any sane logit
-  return __float2int_rz(v);
-}
+// Fused decode + threshold + pixel scaling + truncation + tl/br + compaction.
+// One CTA owns CAND_BOXES consecutive boxes of ONE image: passing boxes are collected in shared
+// memory, the CTA reserves its output range with a single global atomic (per-box atomics on the
+// 64 per-image counters serialise in L2 — measured 10x slower), then copies the records out.
+static constexpr int CAND_BOXES = 128;
 
 __global__ void __launch_bounds__(256)
 decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
                     const int* __restrict__ orig_hw, y3_cand* __restrict__ cands,
                     int* __restrict__ counts, int cap) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;; wid += warps) {
-    int img, a, row, col, m;
-    if (!next_box(d, wid, img, a, row, col, m)) break;
+  __shared__ uint4 s_rec[CAND_BOXES][2];
+  __shared__ int s_count, s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int img = blockIdx.y;
+  const int cells = d.g_h * d.g_w;
+  const int per_img = d.num_anchors * cells;
+  const int m_begin = blockIdx.x * CAND_BOXES;
+  const int m_end = min(m_begin + CAND_BOXES, per_img);
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
+  for (int m = m_begin + warp; m < m_end; m += 8) {
+    const int a = m / cells;
+    const int cell = m - a * cells;
+    const int row = cell / d.g_w;
+    const int col = cell - row * d.g_w;
     const BoxOut o = decode_box(d, logits, img, a, row, col, lane);
     if (lane == 0 && o.prob >= prob_thresh) {  // inference.py:342
-      const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
       const int cx = f2i_trunc(__fmul_rn(o.x, ow));  // inference.py:351-353
       const int cy = f2i_trunc(__fmul_rn(o.y, oh));
       const int bw = f2i_trunc(__fmul_rn(o.w, ow));
       const int bh = f2i_trunc(__fmul_rn(o.h, oh));
       // cxywh_to_tlbr: c -/+ wh // 2 (floor division; wh >= 0)
       const int hw = bw >> 1, hh = bh >> 1;
-      const int slot = atomicAdd(counts + img, 1);
-      if (slot < cap) {
-        y3_cand c;
-        c.x1 = cx - hw; c.y1 = cy - hh; c.x2 = cx + hw; c.y2 = cy + hh;
-        c.prob = o.prob; c.cls = o.cls; c.box = d.box_offset + m; c.pad_ = 0;
-        reinterpret_cast<uint4*>(cands + (long long)img * cap + slot)[0] =
-            make_uint4((uint32_t)c.x1, (uint32_t)c.y1, (uint32_t)c.x2, (uint32_t)c.y2);
-        reinterpret_cast<uint4*>(cands + (long long)img * cap + slot)[1] =
-            make_uint4(__float_as_uint(c.prob), (uint32_t)c.cls, (uint32_t)c.box, 0u);
-      }
+      const int slot = atomicAdd(&s_count, 1);
+      s_rec[slot][0] = make_uint4((uint32_t)(cx - hw), (uint32_t)(cy - hh), (uint32_t)(cx + hw), (uint32_t)(cy + hh));
+      s_rec[slot][1] = make_uint4(__float_as_uint(o.prob), (uint32_t)o.cls, (uint32_t)(d.box_offset + m), 0u);
     }
+  }
+  __syncthreads();
+  const int n = s_count;
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(counts + img, n);
+  __syncthreads();
+  const int base = s_base;
+  uint4* dst = reinterpret_cast<uint4*>(cands + (long long)img * cap);
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+    const int slot = base + (i >> 1);
+    if (slot < cap) dst[2 * (long long)slot + (i & 1)] = s_rec[i >> 1][i & 1];
   }
 }
 
@@ -180,8 +200,9 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits, float prob_
   if (rc != Y3_OK) return rc;
   Y3_CHECK_ARG(orig_hw && cands && counts && cap > 0, "decode_cands: bad output arguments");
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0, "decode_cands: cands must be 16-byte aligned");
-  decode_cands_kernel<<<decode_grid(d), 256, 0, (cudaStream_t)stream>>>(*d, logits, prob_thresh, orig_hw, cands,
-                                                                         counts, cap);
+  const int per_img = d->num_anchors * d->g_h * d->g_w;
+  const dim3 grid((per_img + CAND_BOXES - 1) / CAND_BOXES, d->n);
+  decode_cands_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, logits, prob_thresh, orig_hw, cands, counts, cap);
   Y3_LAUNCH_OK("decode_cands_kernel");
   return Y3_OK;
 }

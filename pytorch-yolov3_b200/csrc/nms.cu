@@ -28,9 +28,17 @@ __device__ __forceinline__ bool iou_gt(const Box4& a, const Box4& b, double thr)
   iw = iw > 0 ? iw : 0;
   ih = ih > 0 ? ih : 0;
   const long long inter = iw * ih;
+  if (inter == 0) return 0.0 > thr;  // disjoint boxes: iou is exactly 0
   const long long uni = area_a + area_b - inter;
-  const double iou = __ddiv_rn((double)inter, (double)uni);
-  return iou > thr;
+  // iou > thr  <=>  fl(inter/uni) > thr.  Away from the boundary the comparison is decided by one
+  // fp64 multiply (inter, uni < 2^53 are exact; the product carries <= 2^-53 relative error); only
+  // within 2^-49 of it the exact IEEE divide the reference performs is evaluated.
+  const double di = (double)inter, du = (double)uni;
+  const double t = thr * du;
+  const double slack = fabs(t) * 1.8e-15;
+  if (di > t + slack) return true;
+  if (di < t - slack) return false;
+  return __ddiv_rn(di, du) > thr;
 }
 
 // workspace layout (int32 words): seg_off [N][C+1] | cursor [N][C]
@@ -276,7 +284,9 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
     Y3_CUDA_OK(cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
-  const int threads = per_class ? 128 : 1024;
+  // small per-class segments dominate real workloads; 512 threads keep the O(n^2) IoU phase of an
+  // occasional huge segment (thousands of boxes of one class, all kept) off the critical path
+  const int threads = per_class ? 512 : 1024;
   nms_segment_kernel<<<dim3(C, n), threads, smem, s>>>(bucketed, seg_off, cap, C, iou_thresh, sorted, keep);
   Y3_LAUNCH_OK("nms_segment_kernel");
   return Y3_OK;

@@ -177,6 +177,67 @@ __global__ void pack_bgr_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16*
   }
 }
 
+// First-layer im2col: a 3x3 / stride 1 / pad 1 convolution over <= 3 input channels has K = 27,
+// which the tensor cores take as one K=32 block.  These kernels write, per pixel, the 27 taps
+// (order r, s, c — the weight layout [Cout][R][S][Cin]) + zero padding as one 64-byte row, so
+// the first convolution runs as a plain GEMM instead of 9 narrow (32-byte-row) im2col TMA loads.
+template <int C, typename Load>
+__device__ __forceinline__ void im2col3x3_pixel(Load load, int h, int w, int y, int x,
+                                                __nv_bfloat16* __restrict__ dst, int k_pad) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = y + r - 1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = x + s - 1;
+      const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) v[(r * 3 + s) * C + cc] = in ? load(iy, ix, cc) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q * 8 < k_pad)
+      st_16(dst + q * 8, make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+}
+
+template <int C>
+__global__ void im2col3x3_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
+                                          int h, int w, int k_pad) {
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % w);
+    const int py = (int)((i / w) % h);
+    const int img = (int)(i / ((long long)w * h));
+    const float* base = x + (long long)img * C * h * w;
+    im2col3x3_pixel<C>([&](int iy, int ix, int cc) { return __ldg(base + ((long long)cc * h + iy) * w + ix); }, h, w,
+                       py, px, y + i * k_pad, k_pad);
+  }
+}
+
+__global__ void im2col3x3_bgr_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
+                                        int w, int k_pad) {
+  const long long total = (long long)n * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % w);
+    const int py = (int)((i / w) % h);
+    const int img = (int)(i / ((long long)w * h));
+    const uint8_t* base = x + (long long)img * h * w * 3;
+    // channel cc of the network input is RGB: R = byte 2, G = byte 1, B = byte 0 (inference.py:332)
+    // v * fl(1/255) rounds to the same bf16 as the reference's fp32 v / 255 for all 256 byte
+    // values (checked exhaustively in tests/test_host_logic.py), without 27 IEEE divides per pixel
+    im2col3x3_pixel<3>([&](int iy, int ix, int cc) {
+      return __fmul_rn((float)__ldg(base + ((long long)iy * w + ix) * 3 + (2 - cc)), 0.003921568859368563f); },
+                       h, w, py, px, y + i * k_pad, k_pad);
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace y3
@@ -275,6 +336,33 @@ int y3_pack_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h, int32_t w, i
   const long long work = (long long)n * h * w;
   pack_bgr_u8_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, work, c_pad);
   Y3_LAUNCH_OK("pack_bgr_u8_kernel");
+  return Y3_OK;
+}
+
+int y3_im2col3x3_nchw_f32(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, int32_t k_pad,
+                          void* stream) {
+  Y3_CHECK_ARG(x && y, "im2col3x3_nchw_f32: null pointer");
+  Y3_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && 9 * c <= k_pad && k_pad <= 32 && k_pad % 8 == 0,
+               "im2col3x3_nchw_f32: need 9*c <= k_pad <= 32 (c=%d k_pad=%d)", c, k_pad);
+  Y3_CHECK_ARG(aligned16(y), "im2col3x3_nchw_f32: alignment");
+  const long long work = (long long)n * h * w;
+  const int grid = grid_for(work, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c == 3) im2col3x3_nchw_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
+  else if (c == 2) im2col3x3_nchw_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
+  else im2col3x3_nchw_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
+  Y3_LAUNCH_OK("im2col3x3_nchw_f32_kernel");
+  return Y3_OK;
+}
+
+int y3_im2col3x3_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h, int32_t w, int32_t k_pad, void* stream) {
+  Y3_CHECK_ARG(x && y, "im2col3x3_bgr_u8: null pointer");
+  Y3_CHECK_ARG(n > 0 && h > 0 && w > 0 && k_pad == 32, "im2col3x3_bgr_u8: k_pad must be 32");
+  Y3_CHECK_ARG(aligned16(y), "im2col3x3_bgr_u8: alignment");
+  const long long work = (long long)n * h * w;
+  im2col3x3_bgr_u8_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, h, w,
+                                                                                  k_pad);
+  Y3_LAUNCH_OK("im2col3x3_bgr_u8_kernel");
   return Y3_OK;
 }
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
 EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
     "y3_conv2d", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
-    "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
+    "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept",
 )
 
@@ -70,6 +70,8 @@ def lib():
     L.y3_upsample2x.argtypes = [c_void_p] * 2 + [c_int32] * 6 + [c_void_p]
     L.y3_pack_nchw_f32.argtypes = [c_void_p] * 2 + [c_int32] * 5 + [c_void_p]
     L.y3_pack_bgr_u8.argtypes = [c_void_p] * 2 + [c_int32] * 4 + [c_void_p]
+    L.y3_im2col3x3_nchw_f32.argtypes = [c_void_p] * 2 + [c_int32] * 5 + [c_void_p]
+    L.y3_im2col3x3_bgr_u8.argtypes = [c_void_p] * 2 + [c_int32] * 4 + [c_void_p]
     L.y3_yolo_decode_dense.argtypes = [POINTER(HeadDesc)] + [c_void_p] * 5
     L.y3_yolo_decode_cands.argtypes = [POINTER(HeadDesc), c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p]
@@ -166,6 +168,17 @@ def pack_bgr_u8(x, y, c_pad):
     n, h, w, c = x.shape
     assert c == 3
     _check(lib().y3_pack_bgr_u8(_ptr(x), _ptr(y), n, h, w, c_pad, _stream()))
+
+
+def im2col3x3_nchw_f32(x, y, k_pad):
+    n, c, h, w = x.shape
+    _check(lib().y3_im2col3x3_nchw_f32(_ptr(x), _ptr(y), n, c, h, w, k_pad, _stream()))
+
+
+def im2col3x3_bgr_u8(x, y, k_pad):
+    n, h, w, c = x.shape
+    assert c == 3
+    _check(lib().y3_im2col3x3_bgr_u8(_ptr(x), _ptr(y), n, h, w, k_pad, _stream()))
 
 
 def make_head_desc(n, g_h, g_w, anchors, num_classes, ld, box_offset, boxes_per_image, train_w, train_h):

@@ -181,11 +181,19 @@ class Engine:
             self._keep.append(buf)
             return View(buf, _p(buf), cs, cs, H, W, f32)
 
-        # network input: channels padded to 16 for the tensor-core path
-        cin_pad = _ceil(cin0, 16)
+        # network input.  A first layer that is 3x3/s1/pad1 over <= 3 channels (every shipped cfg)
+        # gets its im2col done by the packing kernel: the input buffer holds K = 27 -> 32 taps
+        # per pixel and block 0 runs as a plain K=32 GEMM.  Otherwise channels are padded to 16.
+        b0 = blocks[0]
+        self.first_im2col = (b0["type"] == "convolutional" and b0["size"] == 3 and b0["stride"] == 1
+                             and "pad" in b0 and 9 * cin0 <= 32
+                             and os.environ.get("Y3_NO_FIRST_IM2COL", "0") != "1")
+        cin_pad = 32 if self.first_im2col else _ceil(cin0, 16)
         in_buf = torch.zeros(B, self.H, self.W, cin_pad, device=dev, dtype=torch.bfloat16)
         views[INPUT] = View(in_buf, _p(in_buf), cin_pad, cin_pad, self.H, self.W)
         self.in_view = views[INPUT]
+        # channels of the input buffer that hold the image itself (centre tap when im2col'ed)
+        self.input_image_channels = (4 * cin0, 5 * cin0) if self.first_im2col else (0, cin0)
 
         ops = []          # closures, executed in order
         self.op_names = []
@@ -225,8 +233,10 @@ class Engine:
                 if tgt != i:
                     views[i] = yv  # never read (single consumer), kept for introspection
                 res = views[residual_of[i]] if i in residual_of else None
-                w, bias = folded(i, xin.C, cout_pad)
-                kw = dict(n=B, h=xin.H, w_in=xin.W, cin=xin.C, cout=cout_pad, ksize=k, stride=s, pad=pad,
+                as_gemm = self.first_im2col and i == 0
+                w, bias = folded(i, xin.C, cout_pad, flatten_taps=as_gemm)
+                kk, pp = (1, 0) if as_gemm else (k, pad)
+                kw = dict(n=B, h=xin.H, w_in=xin.W, cin=xin.C, cout=cout_pad, ksize=kk, stride=s, pad=pp,
                           ld_x=xin.ld, ld_y=yv.ld, leaky=b["activation"] == "leaky",
                           res_ptr=res.ptr if res else None, ld_res=res.ld if res else 0, out_f32=head,
                           upsample2x=up)
@@ -343,11 +353,12 @@ class Engine:
         ws_bytes = 0 if self.dry else _lib.nms_workspace_bytes(B, M, classes)
         self.nms_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
 
-    def _folded_weights(self, i, cin_store, cout_store):
+    def _folded_weights(self, i, cin_store, cout_store, flatten_taps=False):
         """BN-folded bf16 ``[cout_store][R][S][cin_store]`` weights + fp32 bias of conv block ``i``
-        (shared between plans of one network; a4 in SURVEY.md §8a)."""
+        (shared between plans of one network; a4 in SURVEY.md §8a).  flatten_taps: the (r, s, c)
+        taps become ONE K axis padded to cin_store (first layer run as a GEMM on im2col'ed input)."""
         cache = self.net.__dict__.setdefault("_folded_cache", {})
-        key = (self.net._weights_version, i, cin_store, cout_store, str(self.device))
+        key = (self.net._weights_version, i, cin_store, cout_store, str(self.device), flatten_taps)
         if key in cache:
             return cache[key]
         seq = self.net.modules_[i]
@@ -364,8 +375,12 @@ class Engine:
             else:
                 bias = conv.bias.detach().to(self.device, torch.float32)
             cout, cin, k, _ = W.shape
-            Wk = torch.zeros(cout_store, k, k, cin_store, device=self.device, dtype=torch.float32)
-            Wk[:cout, :, :, :cin] = W.permute(0, 2, 3, 1)
+            if flatten_taps:
+                Wk = torch.zeros(cout_store, 1, 1, cin_store, device=self.device, dtype=torch.float32)
+                Wk[:cout, 0, 0, :k * k * cin] = W.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
+            else:
+                Wk = torch.zeros(cout_store, k, k, cin_store, device=self.device, dtype=torch.float32)
+                Wk[:cout, :, :, :cin] = W.permute(0, 2, 3, 1)
             bf = torch.zeros(cout_store, device=self.device, dtype=torch.float32)
             bf[:cout] = bias
             out = (Wk.to(torch.bfloat16).contiguous(), bf.contiguous())
@@ -396,19 +411,21 @@ class Engine:
 
     def _program(self, key):
         kind = key[0]
+        pack_f32 = _lib.im2col3x3_nchw_f32 if self.first_im2col else _lib.pack_nchw_f32
+        pack_u8 = _lib.im2col3x3_bgr_u8 if self.first_im2col else _lib.pack_bgr_u8
         if kind == "dense_f32":
             def fn():
-                _lib.pack_nchw_f32(self.in_f32, self.in_view.buf, self.in_view.C)
+                pack_f32(self.in_f32, self.in_view.buf, self.in_view.C)
                 self.run_backbone()
                 self._decode_dense()
         elif kind == "det_u8":
             def fn():
-                _lib.pack_bgr_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
                 self.run_backbone()
                 self._detect_tail(key[1], key[2])
         elif kind == "det_f32":
             def fn():
-                _lib.pack_nchw_f32(self.in_f32, self.in_view.buf, self.in_view.C)
+                pack_f32(self.in_f32, self.in_view.buf, self.in_view.C)
                 self.run_backbone()
                 self._detect_tail(key[1], key[2])
         else:

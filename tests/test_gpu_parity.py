@@ -463,8 +463,9 @@ def teacher_forced_network_check(net, blocks, params, B, size):
             continue
         src = alias_root(blocks, i - 1)
         xin = view_to_nchw(eng.views[src], B)
-        if src < 0:
-            xin = xin[:, :3]  # network input is stored padded to 16 channels
+        if src < 0:  # network input: stored channel-padded, or im2col'ed (image = centre tap)
+            c_lo, c_hi = eng.input_image_channels
+            xin = xin[:, c_lo:c_hi]
         with torch.no_grad():
             ref = DO.conv_block(xin, b, params[i])
             nxt = blocks[i + 1] if i + 1 < len(blocks) else {"type": ""}
@@ -551,3 +552,22 @@ def test_yolov3_tiny_416_end_to_end(tmp_path_factory):
     for thr in (0.99, 0.5):
         m, t = match_rate(res, full, thr)
         print(f"yolov3-tiny@416 e2e vs fp32 oracle: {m}/{t} detections matched at IoU>={thr}, same class (reported)")
+
+
+def test_first_layer_im2col_packing_matches_unfold():
+    """K8 (preprocess row): uint8 BGR / float NCHW -> 27-tap rows the first conv consumes as a GEMM."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, 9, 11, generator=g)
+    y = torch.empty(2, 9, 11, 32, device=dev(), dtype=torch.bfloat16)
+    _lib.im2col3x3_nchw_f32(x.to(dev()), y, 32)
+    torch.cuda.synchronize()
+    # F.unfold orders (c, r, s); the kernel writes (r, s, c)
+    ref = F.unfold(x, 3, padding=1).reshape(2, 3, 9, 9 * 11).permute(0, 3, 2, 1).reshape(2, 9, 11, 27)
+    got = y.float().cpu()
+    assert torch.equal(got[..., :27], ref.bfloat16().float()) and float(got[..., 27:].abs().max()) == 0
+    u = torch.randint(0, 256, (2, 9, 11, 3), generator=g, dtype=torch.uint8)
+    _lib.im2col3x3_bgr_u8(u.to(dev()), y, 32)
+    torch.cuda.synchronize()
+    xf = torch.from_numpy(PO.preprocess(list(u.numpy())))  # the reference's own conversion
+    ref = F.unfold(xf, 3, padding=1).reshape(2, 3, 9, 9 * 11).permute(0, 3, 2, 1).reshape(2, 9, 11, 27)
+    assert torch.equal(y.float().cpu()[..., :27], ref.bfloat16().float())

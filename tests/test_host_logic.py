@@ -185,3 +185,11 @@ def test_product_never_imports_the_oracle():
     for m in re.finditer(r"^.*\boracle\b.*$", bench, re.M):
         line = m.group(0)
         assert "cpu_baseline" in line or "reference" in line or line.lstrip().startswith(("#", '"', "from oracle", "import oracle")), line
+
+
+def test_u8_scale_by_reciprocal_is_exact_after_bf16_rounding():
+    """The im2col packing kernel multiplies by fl(1/255) instead of dividing by 255
+    (yolov3/inference.py:333): identical bf16 result for every possible byte."""
+    v = torch.arange(256, dtype=torch.float32)
+    assert torch.equal((v / 255.0).bfloat16(), (v * np.float32(0.003921568859368563)).bfloat16())
+    assert np.float32(0.003921568859368563) == np.float32(1.0) / np.float32(255.0)
