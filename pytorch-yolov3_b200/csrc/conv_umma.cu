@@ -64,7 +64,10 @@ struct ConvCfg {
   static constexpr int EPI_COLS = EPI_SPAN / 2;                            // columns per block
   static constexpr int EPI_BLOCKS = BLOCK_N / EPI_COLS;
   static constexpr int EPI_BLOCK_BYTES = BLOCK_M * EPI_SPAN;
-  static constexpr int STAGING_BYTES = STAGED ? BLOCK_M * BLOCK_N * 2 : 0;
+  // two slabs when they are small, so tile i+1's epilogue does not wait for tile i's TMA store
+  static constexpr int SLAB_BYTES = BLOCK_M * BLOCK_N * 2;
+  static constexpr int STAGING_BUFS = BLOCK_N <= 128 ? 2 : 1;
+  static constexpr int STAGING_BYTES = STAGED ? STAGING_BUFS * SLAB_BYTES : 0;
   static constexpr int SMEM_LIMIT = 232448 - 1024 /*align slack*/ - 256 /*barriers*/;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
@@ -226,12 +229,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // 16-byte units are XOR-swizzled exactly as CU_TENSOR_MAP_SWIZZLE_{128,64,32}B does.
         constexpr int SPAN = Cfg::EPI_SPAN;
         const uint32_t swz = SPAN == 128 ? (row & 7) : SPAN == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);
-        const uint32_t row_base = staging_base + row * SPAN;
-        const uint32_t warp_base = staging_base + quarter * 32 * SPAN;
+        const uint32_t slab = staging_base + (Cfg::STAGING_BUFS == 2 ? (it & 1) * Cfg::SLAB_BYTES : 0);
+        const uint32_t row_base = slab + row * SPAN;
+        const uint32_t warp_base = slab + quarter * 32 * SPAN;
         const bool has_res = p.res != nullptr;
         if (lane == 0) {
-          // the previous tile's TMA stores must have finished READING the slab before it is reused
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          // the TMA stores that last used this slab must have finished READING it before reuse
+          if (Cfg::STAGING_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           if (has_res) {
             ptx::mbar_arrive_expect_tx(res_bar(quarter), 32 * BLOCK_N * 2);
 #pragma unroll

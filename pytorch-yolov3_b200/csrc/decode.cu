@@ -105,10 +105,13 @@ decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
 }
 
 // Fused decode + threshold + pixel scaling + truncation + tl/br + compaction.
-// One CTA owns CAND_BOXES consecutive boxes of ONE image: passing boxes are collected in shared
-// memory, the CTA reserves its output range with a single global atomic (per-box atomics on the
-// 64 per-image counters serialise in L2 — measured 10x slower), then copies the records out.
-static constexpr int CAND_BOXES = 128;
+// One CTA owns CAND_BOXES consecutive boxes of ONE image, 32 per warp.  Phase 1 (cooperative):
+// for each of its boxes the warp reads the logits coalesced and reduces max / argmax / softmax
+// denominator with shuffles, parking the box's raw fields in lane b.  Phase 2 (lane-parallel):
+// lane b finishes box b (sigmoid, exp, scaling, truncation) — 32 boxes per instruction instead
+// of one.  Passing boxes are collected in shared memory; the CTA reserves its output range with
+// a single global atomic (per-box atomics on the per-image counters serialise in L2).
+static constexpr int CAND_BOXES = 256;
 
 __global__ void __launch_bounds__(256)
 decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
@@ -120,27 +123,68 @@ decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
   const int img = blockIdx.y;
   const int cells = d.g_h * d.g_w;
   const int per_img = d.num_anchors * cells;
-  const int m_begin = blockIdx.x * CAND_BOXES;
-  const int m_end = min(m_begin + CAND_BOXES, per_img);
+  const int fields = 5 + d.num_classes;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
-  for (int m = m_begin + warp; m < m_end; m += 8) {
+
+  // ---- phase 1: box b of this warp -> lane b -----------------------------------------------
+  const int m_warp = blockIdx.x * CAND_BOXES + warp * 32;
+  float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, to = 0.f, sum = 1.f;
+  int cls = 0;
+  const int nb = min(32, per_img - m_warp);
+  for (int b = 0; b < nb; ++b) {
+    const int m = m_warp + b;
+    const int a = m / cells;
+    const int cell = m - a * cells;  // row * g_w + col: pixels are contiguous in NHWC
+    const float* px = logits + ((long long)img * cells + cell) * d.ld + a * fields;
+    const float head = (lane < fields) ? __ldg(px + lane) : 0.f;
+    float best = -INFINITY;
+    int best_idx = 0x7fffffff;
+    for (int f = lane; f < fields; f += 32) {
+      const float v = (f == lane) ? head : __ldg(px + f);
+      if (f >= 5 && v > best) { best = v; best_idx = f - 5; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // first index wins ties, like torch.max
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+      if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
+    }
+    float part = 0.f;
+    for (int f = lane; f < fields; f += 32) {
+      if (f >= 5) part += expf(((f == lane) ? head : __ldg(px + f)) - best);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float h0 = __shfl_sync(0xffffffffu, head, 0), h1 = __shfl_sync(0xffffffffu, head, 1);
+    const float h2 = __shfl_sync(0xffffffffu, head, 2), h3 = __shfl_sync(0xffffffffu, head, 3);
+    const float h4 = __shfl_sync(0xffffffffu, head, 4);
+    if (lane == b) { tx = h0; ty = h1; tw = h2; th = h3; to = h4; sum = part; cls = best_idx; }
+  }
+
+  // ---- phase 2: lane b finishes box b ---------------------------------------------------------
+  if (lane < nb) {
+    const int m = m_warp + lane;
     const int a = m / cells;
     const int cell = m - a * cells;
     const int row = cell / d.g_w;
     const int col = cell - row * d.g_w;
-    const BoxOut o = decode_box(d, logits, img, a, row, col, lane);
-    if (lane == 0 && o.prob >= prob_thresh) {  // inference.py:342
-      const int cx = f2i_trunc(__fmul_rn(o.x, ow));  // inference.py:351-353
-      const int cy = f2i_trunc(__fmul_rn(o.y, oh));
-      const int bw = f2i_trunc(__fmul_rn(o.w, ow));
-      const int bh = f2i_trunc(__fmul_rn(o.h, oh));
-      // cxywh_to_tlbr: c -/+ wh // 2 (floor division; wh >= 0)
-      const int hw = bw >> 1, hh = bh >> 1;
+    // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)  (darknet.py:104-108)
+    const float prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
+    if (prob >= prob_thresh) {  // inference.py:342
+      const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
+      const float x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)d.g_w);
+      const float y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)d.g_h);
+      const float w = __fdiv_rn(__fmul_rn(expf(tw), d.anchor_w[a]), d.train_w);
+      const float h = __fdiv_rn(__fmul_rn(expf(th), d.anchor_h[a]), d.train_h);
+      const int cx = f2i_trunc(__fmul_rn(x, ow));  // inference.py:351-353
+      const int cy = f2i_trunc(__fmul_rn(y, oh));
+      const int bw = f2i_trunc(__fmul_rn(w, ow));
+      const int bh = f2i_trunc(__fmul_rn(h, oh));
+      const int hw = bw >> 1, hh = bh >> 1;  // cxywh_to_tlbr: c -/+ wh // 2 (wh >= 0)
       const int slot = atomicAdd(&s_count, 1);
       s_rec[slot][0] = make_uint4((uint32_t)(cx - hw), (uint32_t)(cy - hh), (uint32_t)(cx + hw), (uint32_t)(cy + hh));
-      s_rec[slot][1] = make_uint4(__float_as_uint(o.prob), (uint32_t)o.cls, (uint32_t)(d.box_offset + m), 0u);
+      s_rec[slot][1] = make_uint4(__float_as_uint(prob), (uint32_t)cls, (uint32_t)(d.box_offset + m), 0u);
     }
   }
   __syncthreads();

@@ -5,10 +5,11 @@
 //   1. nms_bucket_kernel   one CTA per image: class histogram in shared memory, exclusive
 //                          scan, scatter of the candidates into per-class segments.
 //   2. nms_segment_kernel  one CTA per (image, class) segment: rank-sort the segment by
-//                          (prob desc, box asc), then greedy suppression in chunks of 32
-//                          pivots — warp 0 builds the 32x32 IoU bitmask of a chunk with
-//                          shuffles and resolves it with ballots, then every thread tests its
-//                          later boxes against the chunk's KEPT pivots only.
+//                          (prob desc, box asc); segments of <= 512 boxes build the full
+//                          "i suppresses j" bit matrix in shared memory (ballot per 32 boxes) and
+//                          one warp scans it in score order; larger segments go 32 pivots at a
+//                          time (32x32 mask by shuffles, resolved with ballots, then every thread
+//                          tests its later boxes against the chunk's KEPT pivots only).
 //   3. nms_compact_kernel  ordered compaction of the kept records (block scan).
 // IoU follows the reference exactly: "+1" pixel areas in int64, iou = inter/union as an IEEE
 // float64 divide, suppressed iff iou > thresh.
@@ -94,10 +95,21 @@ __device__ __forceinline__ bool before(float pa, int ba, float pb, int bb) {
   return pa > pb || (pa == pb && ba < bb);
 }
 
+// Segments of up to BITMASK_MAX boxes (every realistic per-class segment) take the bitmask path:
+// all threads fill the n x n/32 "i suppresses j" bit matrix in shared memory (one IoU test per
+// lane, rows reduced with __ballot_sync), then ONE warp walks the boxes in score order keeping
+// the running "removed" set as one 32-bit word per lane.  Larger segments (class-agnostic NMS
+// over thousands of boxes) use the chunked pivot scheme below.
+static constexpr int BITMASK_MAX = 512;
+static constexpr int BITMASK_WORDS = BITMASK_MAX / 32;
+
 __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
                                    int cap, int C, double thr, y3_cand* __restrict__ sorted,
-                                   uint8_t* __restrict__ keep) {
-  extern __shared__ uint8_t alive[];  // one byte per box of the segment
+                                   uint8_t* __restrict__ keep, int alive_bytes) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  uint8_t* alive = dyn_smem;                                              // [alive_bytes] (large path)
+  int4* sbox = reinterpret_cast<int4*>(dyn_smem + alive_bytes);           // [BITMASK_MAX]
+  uint32_t* smask = reinterpret_cast<uint32_t*>(sbox + BITMASK_MAX);      // [BITMASK_MAX][BITMASK_WORDS]
   __shared__ uint32_t kept_mask_s;
   const int img = blockIdx.y;
   const int seg = blockIdx.x;
@@ -107,8 +119,12 @@ __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const i
   const y3_cand* src = bucketed + (long long)img * cap + off;
   y3_cand* out = sorted + (long long)img * cap + off;
   uint8_t* keep_out = keep + (long long)img * cap + off;
+  const bool small = n <= BITMASK_MAX;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
 
-  // ---- rank sort --------------------------------------------------------------------
+  // ---- rank sort by (prob desc, box asc) ------------------------------------------------
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
     const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
@@ -121,13 +137,46 @@ __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const i
     }
     reinterpret_cast<uint4*>(out + rank)[0] = lo;
     reinterpret_cast<uint4*>(out + rank)[1] = hi;
-    alive[i] = 1;
+    if (small) sbox[rank] = make_int4((int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w);
+    else alive[i] = 1;
   }
   __syncthreads();  // global writes to `out` by this CTA are visible to it from here on
 
-  // ---- greedy suppression, 32 pivots at a time ------------------------------------------
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  if (small) {
+    // ---- bit matrix: word (i, w) holds, for j = 32w + lane, [j > i and iou(i, j) > thr] ----
+    const int words = (n + 31) >> 5;
+    for (int item = warp; item < n * words; item += nwarps) {
+      const int i = item / words;
+      const int w = item - i * words;
+      if (32 * w + 31 <= i) {  // every j of this word precedes i: nothing to suppress
+        if (lane == 0) smask[i * BITMASK_WORDS + w] = 0u;
+        continue;
+      }
+      const int j = 32 * w + lane;
+      bool sup = false;
+      if (j < n && j > i) {
+        const int4 bi = sbox[i], bj = sbox[j];
+        sup = iou_gt(Box4{bi.x, bi.y, bi.z, bi.w}, Box4{bj.x, bj.y, bj.z, bj.w}, thr);
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0) smask[i * BITMASK_WORDS + w] = word;
+    }
+    __syncthreads();
+    // ---- greedy scan: lane w owns bits [32w, 32w+32) of the removed set ---------------------
+    if (warp == 0) {
+      uint32_t removed = 0;
+      for (int i = 0; i < n; ++i) {
+        const uint32_t row = (lane < words) ? smask[i * BITMASK_WORDS + lane] : 0u;  // independent of `removed`
+        const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
+        const bool kept = ((r >> (i & 31)) & 1u) == 0;
+        if (kept) removed |= row;
+        if (lane == 0) keep_out[i] = kept ? 1 : 0;
+      }
+    }
+    return;
+  }
+
+  // ---- large segment: greedy suppression, 32 pivots at a time ----------------------------
   for (int c0 = 0; c0 < n; c0 += 32) {
     if (warp == 0) {
       const int j = c0 + lane;
@@ -277,17 +326,18 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
                                        class_first_box);
   Y3_LAUNCH_OK("nms_bucket_kernel");
 
-  // alive[] needs one byte per box of the largest possible segment (= cap)
-  const size_t smem = ((size_t)cap + 15) / 16 * 16;
+  // dynamic smem: alive[] (one byte per box of the largest possible segment = cap, large path)
+  // + boxes and bit matrix of the bitmask path
+  const int alive_bytes = (int)(((size_t)cap + 15) / 16 * 16);
+  const size_t smem = (size_t)alive_bytes + BITMASK_MAX * sizeof(int4) + (size_t)BITMASK_MAX * BITMASK_WORDS * 4;
   static size_t smem_attr = 0;
-  if (smem > 48 * 1024 && smem > smem_attr) {
+  if (smem > smem_attr) {
     Y3_CUDA_OK(cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
-  // small per-class segments dominate real workloads; 512 threads keep the O(n^2) IoU phase of an
-  // occasional huge segment (thousands of boxes of one class, all kept) off the critical path
-  const int threads = per_class ? 512 : 1024;
-  nms_segment_kernel<<<dim3(C, n), threads, smem, s>>>(bucketed, seg_off, cap, C, iou_thresh, sorted, keep);
+  const int threads = per_class ? 256 : 1024;
+  nms_segment_kernel<<<dim3(C, n), threads, smem, s>>>(bucketed, seg_off, cap, C, iou_thresh, sorted, keep,
+                                                       alive_bytes);
   Y3_LAUNCH_OK("nms_segment_kernel");
   return Y3_OK;
 }

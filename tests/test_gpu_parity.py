@@ -571,3 +571,15 @@ def test_first_layer_im2col_packing_matches_unfold():
     xf = torch.from_numpy(PO.preprocess(list(u.numpy())))  # the reference's own conversion
     ref = F.unfold(xf, 3, padding=1).reshape(2, 3, 9, 9 * 11).permute(0, 3, 2, 1).reshape(2, 9, 11, 27)
     assert torch.equal(y.float().cpu()[..., :27], ref.bfloat16().float())
+
+
+def test_nms_skewed_classes_cover_bitmask_and_pivot_paths():
+    """Per-class segments on both sides of the 512-box bitmask limit (511, 512, 513, 1500) plus
+    empty classes, against the NumPy oracle (exact order)."""
+    rng = np.random.default_rng(5)
+    sizes = {0: 511, 3: 512, 4: 513, 7: 1500, 9: 1, 11: 40}
+    n = sum(sizes.values())
+    tlbr, prob, _ = stress_candidates(rng, n, 80, 300)
+    cls = rng.permutation(np.concatenate([np.full(k, c) for c, k in sizes.items()])).astype(np.int64)
+    for thr in (0.3, 0.6):
+        assert yolov3_b200.non_max_suppression(tlbr, prob, cls, thr) == PO.nms(tlbr, prob, cls, thr)
