@@ -81,7 +81,8 @@ typedef struct y3_conv_desc {
   int32_t flags;            /* validation knobs, normally 0.  bit0: load A
                                through the im2col tensor map even for 1x1/s1;
                                bit1: use the direct (register->global)
-                               epilogue instead of the staged TMA-store one */
+                               epilogue instead of the staged TMA-store one;
+                               bit2: never use CTA-pair (cta_group::2) tiles */
 } y3_conv_desc;
 
 int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w,

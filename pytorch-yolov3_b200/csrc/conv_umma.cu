@@ -51,10 +51,15 @@ struct ConvKernelParams {
   int leaky, out_f32, upsample;
 };
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED>
+// CG = 1: one CTA per tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares one
+// 256-row tile — each CTA stages its own 128 rows of A and HALF of the weight slab, the leader's
+// MMAs read both halves, so per-SM operand traffic and smem per stage drop by a third and the
+// pipeline gets deep enough to cover L2/HBM latency at full tensor rate.
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
 struct ConvCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CG;  // weight rows staged by THIS CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   // keep every stage 1024B-aligned (required for SWIZZLE_128B, harmless otherwise)
   static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
@@ -79,22 +84,25 @@ struct ConvCfg {
   static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
   static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
   static constexpr uint64_t DESC_HI = ((SBO >> 4) << 32) | (1ull << 46) | (LAYOUT_TYPE << 61);
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128 per CTA (256 for a pair)
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) |
-                                    (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+                                    (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((BLOCK_M * CG) >> 4) << 24);
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t desc_hi) {
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
 }
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED>
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG>;
   constexpr int STAGES = Cfg::STAGES;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int tile_first = blockIdx.x / CG;   // persistent loop over tiles, one CTA (pair) per SM (pair)
+  const int tile_step = gridDim.x / CG;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,22 +129,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (p.res) ptx::prefetch_tensormap(&tmap_r);
     }
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), CG);   // one producer arrival per CTA of the pair (leader's barrier)
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp (of both CTAs)
     }
     for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc<CG>(tmem_ptr_addr, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish<CG>();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();  // peer barriers must be initialised before any remote arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -145,10 +154,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // CG == 2: TMA completions of BOTH CTAs are counted on the leader's full barrier
+      const uint32_t full_base = CG == 2 ? ptx::mapa(full_bar(0), 0) : full_bar(0);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
-        const int m0 = m_tile * BLOCK_M;
+        const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M;
         const int img = m0 / p.HoWo;
         const int rem = m0 - img * p.HoWo;
         const int ho0 = rem / p.Wo;
@@ -160,16 +171,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_STRIDE;
-          ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint32_t fbar = full_base + 8u * stage;
+          if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+          else ptx::mbar_arrive_cluster(fbar);
           if (p.a_tiled) {
-            ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), cb * BLOCK_K, m0);
+            ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, m0);
           } else {
             const int r = tap / p.S;
             const int s = tap - r * p.S;
-            ptx::tma_load_im2col_4d(a_dst, &tmap_a, full_bar(stage), cb * BLOCK_K, w_base, h_base,
-                                    img, (uint16_t)s, (uint16_t)r);
+            ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, w_base, h_base, img, (uint16_t)s,
+                                        (uint16_t)r);
           }
-          ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          ptx::tma_load_2d<CG>(b_dst, &tmap_b, fbar, kb * BLOCK_K,
+                               n_tile * BLOCK_N + (int)cta_rank * Cfg::B_ROWS);
           if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -177,12 +191,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this buffer
@@ -198,13 +212,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the swizzle span: +2 in the >>4 address field
-            ptx::umma_bf16_ss(tmem_d, desc_a + 2u * k, desc_b + 2u * k, Cfg::IDESC,
-                              (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_ss<CG>(tmem_d, desc_a + 2u * k, desc_b + 2u * k, Cfg::IDESC,
+                                  (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+          ptx::umma_commit<CG>(empty_bar(stage));  // smem stage reusable (in both CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(tfull_bar(acc));  // accumulator complete
+        ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete (signalled in both CTAs)
       }
     }
     __syncwarp();
@@ -213,12 +227,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
     const int row = quarter * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    // the accumulator is handed back on the LEADER's barrier (its MMA thread waits there)
+    const uint32_t tempty_base = (CG == 2 && cta_rank != 0) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      const int m0 = m_tile * BLOCK_M;
+      const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M;
       const int m = m0 + row;
       const int n0 = n_tile * BLOCK_N;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BLOCK_N;
@@ -295,7 +311,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          ptx::mbar_arrive(tempty_bar(acc));
+          ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
           if (m0 + quarter * 32 < p.M) {
 #pragma unroll
             for (int cb = 0; cb < Cfg::EPI_BLOCKS; ++cb)
@@ -380,17 +396,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // all TMEM reads of this warp are complete (wait::ld above): hand the buffer back
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
       }
     }
     if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync();  // the peer may still be reading this CTA's smem / signalling it
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    ptx::tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -483,10 +500,10 @@ static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x,
   return Y3_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED>
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
 static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, cudaStream_t stream, int force_im2col) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG>;
   const int ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
   const long long M = (long long)d->n * ho * wo;
@@ -499,7 +516,7 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   p.num_kb = d->ksize * d->ksize * p.cin_blocks;
   p.S = d->ksize;
   p.stride = d->stride; p.pad = d->pad;
-  p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.num_m_tiles = (int)((M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   p.num_n_tiles = d->cout / BLOCK_N;
   p.a_tiled = (d->ksize == 1 && d->stride == 1 && d->pad == 0 && !force_im2col) ? 1 : 0;
   p.bias = bias;
@@ -522,7 +539,7 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   }
   if (rc != Y3_OK) return rc;
   const uint64_t k_total = (uint64_t)d->ksize * d->ksize * d->cin;
-  rc = encode_2d(&tmap_b, w, k_total, (uint64_t)d->cout, k_total * 2, BLOCK_K, BLOCK_N, BLOCK_K);
+  rc = encode_2d(&tmap_b, w, k_total, (uint64_t)d->cout, k_total * 2, BLOCK_K, Cfg::B_ROWS, BLOCK_K);
   if (rc != Y3_OK) return rc;
 
   if (STAGED) {
@@ -537,15 +554,29 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
     }
   }
 
-  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED>;
+  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED, CG>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     Y3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kernel<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmap_a, tmap_b, tmap_y, tmap_r, p);
+  const int slots = num_sms() / CG;  // CTAs (or CTA pairs) resident at once
+  const int grid = CG * (num_tiles < slots ? num_tiles : slots);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  Y3_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_b, tmap_y, tmap_r, p));
   Y3_LAUNCH_OK("conv_umma_kernel");
   return Y3_OK;
 }
@@ -555,8 +586,15 @@ static int dispatch_epi(const y3_conv_desc* d, const void* x, const void* w, con
                         const void* residual, void* y, cudaStream_t stream, int force_im2col) {
   // float32 head logits and the fused 2x upsample use the direct (register -> global) epilogue
   if (d->out_f32 || d->upsample2x || (d->flags & 2))
-    return launch_conv<BLOCK_N, BLOCK_K, false>(d, x, w, bias, residual, y, stream, force_im2col);
-  return launch_conv<BLOCK_N, BLOCK_K, true>(d, x, w, bias, residual, y, stream, force_im2col);
+    return launch_conv<BLOCK_N, BLOCK_K, false, 1>(d, x, w, bias, residual, y, stream, force_im2col);
+  // wide tiles with a deep K loop: CTA pairs (cta_group::2).  flags bit2 forces single-CTA tiles.
+  if constexpr (BLOCK_N == 256 && BLOCK_K == 64) {
+    const long long M = (long long)d->n * ((d->h + 2 * d->pad - d->ksize) / d->stride + 1) *
+                        ((d->w + 2 * d->pad - d->ksize) / d->stride + 1);
+    if (!(d->flags & 4) && M >= 2 * BLOCK_M)
+      return launch_conv<BLOCK_N, BLOCK_K, true, 2>(d, x, w, bias, residual, y, stream, force_im2col);
+  }
+  return launch_conv<BLOCK_N, BLOCK_K, true, 1>(d, x, w, bias, residual, y, stream, force_im2col);
 }
 
 template <int BLOCK_K>

@@ -45,12 +45,45 @@ def _order_like_reference(cls_sorted, first_box_row):
         return np.zeros(0, dtype=np.int64)
     order = _set_order(first_box_row)
     starts = np.searchsorted(cls_sorted, order, side="left")
-    ends = np.searchsorted(cls_sorted, order, side="right")
-    return np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if order else np.zeros(0, np.int64)
+    lens = np.searchsorted(cls_sorted, order, side="right") - starts
+    # concatenation of the ranges [start_k, start_k + len_k) without a Python loop
+    offs = np.cumsum(lens) - lens
+    return np.arange(int(lens.sum()), dtype=np.int64) + np.repeat(starts - offs, lens)
 
 
 def _pinned(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+_copy_pool = None
+
+
+def _stack_into(dst, images):
+    """``np.stack(images)`` straight into the pinned staging buffer; large batches are copied by a
+    few threads (NumPy releases the GIL for contiguous copies)."""
+    global _copy_pool
+    first = images[0].shape
+    for im in images:
+        if im.shape != first:  # the reference fails in np.stack with this error type
+            raise ValueError("all input arrays must have the same shape")
+        if im.dtype != np.uint8:
+            raise ValueError(f"images must be uint8, got {im.dtype}")
+    n = len(images)
+    if n < 8:
+        for i, im in enumerate(images):
+            dst[i] = im
+        return
+    if _copy_pool is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+    workers = _copy_pool._max_workers
+
+    def job(lo):
+        for i in range(lo, n, workers):
+            dst[i] = images[i]
+
+    list(_copy_pool.map(job, range(workers)))
 
 
 def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True):
@@ -77,10 +110,9 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
         import cv2
         net_shape = (net.net_info["height"], net.net_info["width"])
         images = [cv2.resize(im, net_shape) if im.shape[:2] != net_shape else im for im in images]
-    batch = np.stack(images)  # raises ValueError on ragged shapes, like the reference
-    if batch.dtype != np.uint8 or batch.ndim != 4 or batch.shape[3] != 3:
-        raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got {batch.dtype} {batch.shape}")
-    B, H, W, _ = batch.shape
+    if images[0].ndim != 3 or images[0].shape[2] != 3:
+        raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got shape {images[0].shape}")
+    B, (H, W, _) = len(images), images[0].shape
     eng = net.engine(B, H, W)
     if eng.device != dev:
         raise RuntimeError(f"net runs on {eng.device}, inference(device='{device}') requested")
@@ -93,7 +125,7 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
             io["counts"] = _pinned((B,), torch.int32)
             io["first"] = _pinned((B, eng.num_classes), torch.int32)
             io["dets"] = _pinned((B * eng.cap, 8), torch.int32)
-        io["img"].numpy()[...] = batch
+        _stack_into(io["img"].numpy(), images)  # raises ValueError on ragged shapes, like np.stack
         io["hw"].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
         eng.in_u8.copy_(io["img"], non_blocking=True)
         eng.orig_hw.copy_(io["hw"], non_blocking=True)
@@ -109,12 +141,14 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
         rec = io["dets"].numpy()[:total]
         first = io["first"].numpy()
 
+    tlbr_all, prob_all, cls_all, _ = records_to_numpy(rec)  # one conversion for the whole batch
     results, pos = [], 0
     for i in range(B):
-        tlbr, prob, cls, _ = records_to_numpy(rec[pos:pos + counts[i]])
-        pos += counts[i]
+        k = int(counts[i])
+        cls = cls_all[pos:pos + k]
         perm = _order_like_reference(cls, first[i])
-        results.append([tlbr[perm, :], prob[perm], cls[perm]])
+        results.append([tlbr_all[pos:pos + k][perm, :], prob_all[pos:pos + k][perm], cls[perm]])
+        pos += k
     return results
 
 

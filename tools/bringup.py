@@ -32,6 +32,10 @@ CONV_CASES = [
     ("3x3_persistent_676tiles", 8, 104, 104, 64, 128, 3, 1, 1, 0, 0, 0, 0),
     ("3x3_c512_n1024_13", 8, 13, 13, 512, 1024, 3, 1, 1, 0, 0, 0, 0),
     ("1x1_n512", 2, 26, 26, 256, 512, 1, 1, 1, 0, 0, 0, 0),
+    ("3x3_pair_res_52", 4, 52, 52, 128, 256, 3, 1, 1, 1, 0, 0, 0),
+    ("3x3_pair_s2", 4, 52, 52, 256, 512, 3, 2, 1, 0, 0, 0, 0),
+    ("1x1_pair_tail", 3, 13, 13, 512, 256, 1, 1, 1, 0, 0, 0, 0),
+    ("3x3_pair_many_tiles", 16, 52, 52, 128, 256, 3, 1, 1, 1, 0, 0, 0),
 ]
 
 
@@ -63,20 +67,20 @@ def run_conv_case(case):
     r_nhwc = r.permute(0, 2, 3, 1).contiguous() if res else None
     oh, ow = (2 * ho, 2 * wo) if up else (ho, wo)
     out = None
-    for direct in (False, True):
+    for direct, one_cta in ((False, False), (False, True), (True, True)):
         y = torch.full((n, oh, ow, cout), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
         t0 = time.time()
         _lib.conv2d(x_nhwc.data_ptr(), w_krsc, bias, y.data_ptr(), n=n, h=h, w_in=w, cin=cin, cout=cout, ksize=k,
                     stride=s, pad=pad, ld_x=cin, ld_y=cout, leaky=leaky, res_ptr=r_nhwc.data_ptr() if res else None,
                     ld_res=cout, out_f32=bool(f32), upsample2x=bool(up), force_im2col=bool(force),
-                    force_direct=direct)
+                    force_direct=direct, force_1cta=one_cta)
         torch.cuda.synchronize()
         dt = time.time() - t0
         got = y.float().permute(0, 3, 1, 2)
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         nan = int(torch.isnan(got).sum().item())
         ok = nan == 0 and err < 1e-2
-        cur = {"case": name + ("/direct" if direct else "/staged"), "ok": ok, "rel_err": err, "nan": nan,
+        cur = {"case": name + ("/direct" if direct else "/staged") + ("/1cta" if one_cta else "/auto"), "ok": ok, "rel_err": err, "nan": nan,
                "ms_first_call": dt * 1e3}
         if out is None or not ok:
             out = cur
