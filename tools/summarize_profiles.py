@@ -1,0 +1,77 @@
+"""Turn the raw ncu artefacts a gpurun call brings back into the small summaries kept under profiles/.
+
+    python tools/summarize_profiles.py launches gpurun_out/launches.csv profiles/r01_launches_step.csv
+    python tools/summarize_profiles.py raw gpurun_out/prof_conv.ncu-rep profiles/r01_conv_ncu_full.csv
+
+`launches`: the `--metrics gpu__time_duration.sum` list -> every launch of the LAST step (from its
+pack/im2col kernel on) with grid/block/µs, followed by a per-kernel aggregate with the share of the
+step.  `raw`: `ncu -i … --page raw --csv` reduced to the columns the roofline argument uses.
+"""
+import csv
+import collections
+import re
+import subprocess
+import sys
+
+RAW_COLS = [
+    "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+]
+
+
+def short(name):
+    name = name.replace("void ", "").replace("y3::", "")
+    m = re.match(r"([\w:]+(<[^(]*>)?)", name)
+    return (m.group(1) if m else name)[:100]
+
+
+def read_csv_after_header(path):
+    lines = open(path).read().splitlines()
+    i0 = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    return list(csv.DictReader(lines[i0:]))
+
+
+def launches(src, dst):
+    rows = read_csv_after_header(src)
+    recs = [(short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3) for r in rows]
+    starts = [i for i, r in enumerate(recs) if "im2col" in r[0] or "pack" in r[0]]
+    step = recs[starts[-1]:]
+    total = sum(r[3] for r in step)
+    agg = collections.OrderedDict()
+    for n, _, _, us in step:
+        a = agg.setdefault(n, [0.0, 0])
+        a[0] += us
+        a[1] += 1
+    with open(dst, "w") as f:
+        f.write(f"# last step of {src}: {len(step)} launches, {total:.1f} us serialised (ncu, cold cache)\n")
+        f.write("# --- per-kernel aggregate: kernel,launches,us,share_of_step\n")
+        for n, (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{n},{c},{us:.1f},{us / total:.4f}\n")
+        f.write("# --- every launch: idx,kernel,grid,block,us\n")
+        for i, (n, g, b, us) in enumerate(step):
+            f.write(f"{i},{n},\"{g}\",\"{b}\",{us:.2f}\n")
+    print(open(dst).read().split("# --- every")[0])
+
+
+def raw(src, dst):
+    txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    cols = [hdr.index(c) for c in RAW_COLS if c in hdr]
+    with open(dst, "w") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in cols])
+        w.writerow([units[i] for i in cols])
+        for d in data:
+            w.writerow([short(d[i]) if hdr[i] == "Kernel Name" else d[i] for i in cols])
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3])
