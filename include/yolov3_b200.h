@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 1
+#define Y3_ABI_VERSION 2
 
 enum {
   Y3_OK = 0,
@@ -199,13 +199,30 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits,
  * (nullable) int32 [N,num_classes] (or [N,1] when !per_class) = smallest box
  * index among the candidates of each class, INT32_MAX if none — what the
  * host needs to replay the reference's set(class_idx) visiting order.
+ * class_start (nullable) int32 [N,C+1] (C = num_classes, or 1 when
+ * !per_class): first index of each class segment inside the image's `sorted`
+ * row, last entry = number of candidates; class_kept (nullable) int32 [N,C]:
+ * records kept per class segment.
  * workspace: at least y3_nms_workspace_bytes(N, cap, num_classes) bytes.
  */
 size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes);
 int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap,
            int32_t num_classes, double iou_thresh, int32_t per_class,
            y3_cand* sorted, uint8_t* keep, int32_t* class_first_box,
+           int32_t* class_start, int32_t* class_kept,
            void* workspace, size_t workspace_bytes, void* stream);
+
+/* a17: the arrays `inference` returns (yolov3/inference.py:360-366), in their
+ * final dtypes and order, built on the device.  For every (image, segment)
+ * pair — segments as delimited by class_start [N,num_segments+1] from y3_nms
+ * — the kept records (prob descending) are written from position
+ * dst_off[image*num_segments + segment] of the flat outputs (negative: skip):
+ * tlbr int64 [K,4], prob float32 [K], cls int64 [K].  The host chooses dst_off
+ * so that class groups follow the reference's set(class_idx) visiting order. */
+int y3_emit_detections(const y3_cand* sorted, const uint8_t* keep,
+                       const int32_t* class_start, const int32_t* dst_off,
+                       int32_t n, int32_t cap, int32_t num_segments,
+                       int64_t* tlbr, float* prob, int64_t* cls, void* stream);
 
 /* Ordered compaction of the kept records.  det_counts [N] receives the number
  * kept per image.  flat == 0: image i's records start at dets[i*cap];

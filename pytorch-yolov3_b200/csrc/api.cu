@@ -1,6 +1,7 @@
 // api.cu — library-level entry points: version, errors, device check, launch counter.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace y3 {
@@ -16,6 +17,15 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("Y3_NO_PDL");
+    cached = (e && e[0] == '1') ? 0 : 1;
+  }
+  return cached == 1;
+}
 
 int num_sms() {
   static int cached_dev = -1;

@@ -45,9 +45,38 @@ void count_launch(int n = 1);
   } while (0)
 
 int num_sms();  // SM count of the current device (cached per device)
+bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 turns it off)
+
+#ifdef __CUDACC__
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute:
+// kernel i+1's CTAs may become resident (and run their prologue) while kernel i drains, and block
+// in pdl_enter()/pdl_wait() until kernel i has completed and its writes are visible.  Captured
+// into a CUDA graph the attribute becomes a programmatic dependency edge.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch: let the next kernel of the stream start its prologue, then wait
+// until the previous kernel has completed (no-ops when launched without the attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -73,13 +73,14 @@ struct ConvCfg {
   static constexpr int SLAB_BYTES = BLOCK_M * BLOCK_N * 2;
   static constexpr int STAGING_BUFS = BLOCK_N <= 128 ? 2 : 1;
   static constexpr int STAGING_BYTES = STAGED ? STAGING_BUFS * SLAB_BYTES : 0;
-  static constexpr int SMEM_LIMIT = 232448 - 1024 /*align slack*/ - 256 /*barriers*/;
+  static constexpr int SMEM_LIMIT = 232448 - 1024 /*align slack*/ - 512 /*barriers*/;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int MAX_STAGES = 16;  // barrier block: (2*STAGES + 9) * 8 bytes <= 512
+  static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS_RAW = 2 * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
                                  : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
   // UMMA smem descriptor pieces (K-major, swizzle span = BLOCK_K*2 bytes)
   static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
   static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
@@ -121,6 +122,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
+  // PDL: the next kernel's CTAs may take this SM as soon as this CTA leaves; this CTA's own set-up
+  // (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel.
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
@@ -148,6 +152,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_wait();  // everything below reads or writes global memory the previous kernel may still own
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -569,13 +574,15 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   Y3_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmap_a, tmap_b, tmap_y, tmap_r, p));
   Y3_LAUNCH_OK("conv_umma_kernel");
   return Y3_OK;

@@ -89,6 +89,7 @@ __device__ __forceinline__ bool next_box(const y3_head_desc& d, long long wid, i
 __global__ void __launch_bounds__(256)
 decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, float* __restrict__ bbox,
                     float* __restrict__ prob, long long* __restrict__ cls) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;; wid += warps) {
@@ -106,20 +107,26 @@ decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
 
 // Fused decode + threshold + pixel scaling + truncation + tl/br + compaction.
 // One CTA owns CAND_BOXES consecutive boxes of ONE image, 32 per warp.  Phase 1 (cooperative):
-// for each of its boxes the warp reads the logits coalesced and reduces max / argmax / softmax
-// denominator with shuffles, parking the box's raw fields in lane b.  Phase 2 (lane-parallel):
-// lane b finishes box b (sigmoid, exp, scaling, truncation) — 32 boxes per instruction instead
-// of one.  Passing boxes are collected in shared memory; the CTA reserves its output range with
-// a single global atomic (per-box atomics on the per-image counters serialise in L2).
+// EIGHT lanes share a box, so a warp reduces four boxes at a time: lane `sub` of a group loads
+// fields sub, sub+8, ... (all loads of a box are issued before the first use — up to 11 per lane
+// are kept in registers, enough for 5+80 fields; wider heads re-read the remainder), then max /
+// argmax / softmax denominator are reduced over the 8 lanes with three shuffle steps and the raw
+// fields of box b are parked in lane b.  Phase 2 (lane-parallel): lane b finishes box b (sigmoid,
+// exp, scaling, truncation) — 32 boxes per instruction.  Passing boxes are collected in shared
+// memory; the CTA reserves its output range with a single global atomic (per-box atomics on the
+// per-image counters serialise in L2).
 static constexpr int CAND_BOXES = 256;
+static constexpr int DEC_CACHED = 11;  // fields cached per lane: 8 * 11 = 88 >= 5 + 80
 
 __global__ void __launch_bounds__(256)
 decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
                     const int* __restrict__ orig_hw, y3_cand* __restrict__ cands,
                     int* __restrict__ counts, int cap) {
+  pdl_enter();
   __shared__ uint4 s_rec[CAND_BOXES][2];
   __shared__ int s_count, s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, grp = lane >> 3;
   const int img = blockIdx.y;
   const int cells = d.g_h * d.g_w;
   const int per_img = d.num_anchors * cells;
@@ -127,39 +134,58 @@ decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
 
-  // ---- phase 1: box b of this warp -> lane b -----------------------------------------------
+  // ---- phase 1: four boxes per warp iteration; box b of this warp ends up in lane b --------
   const int m_warp = blockIdx.x * CAND_BOXES + warp * 32;
   float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, to = 0.f, sum = 1.f;
   int cls = 0;
   const int nb = min(32, per_img - m_warp);
-  for (int b = 0; b < nb; ++b) {
-    const int m = m_warp + b;
+  for (int it = 0; it * 4 < nb; ++it) {
+    const int b = it * 4 + grp;
+    const bool live = b < nb;
+    const int m = m_warp + (live ? b : 0);
     const int a = m / cells;
     const int cell = m - a * cells;  // row * g_w + col: pixels are contiguous in NHWC
     const float* px = logits + ((long long)img * cells + cell) * d.ld + a * fields;
-    const float head = (lane < fields) ? __ldg(px + lane) : 0.f;
+    float v[DEC_CACHED];
+#pragma unroll
+    for (int i = 0; i < DEC_CACHED; ++i) {
+      const int f = sub + 8 * i;
+      v[i] = (live && f < fields) ? __ldg(px + f) : -INFINITY;
+    }
     float best = -INFINITY;
     int best_idx = 0x7fffffff;
-    for (int f = lane; f < fields; f += 32) {
-      const float v = (f == lane) ? head : __ldg(px + f);
-      if (f >= 5 && v > best) { best = v; best_idx = f - 5; }
+#pragma unroll
+    for (int i = 0; i < DEC_CACHED; ++i) {
+      const int f = sub + 8 * i;
+      if (f >= 5 && f < fields && v[i] > best) { best = v[i]; best_idx = f - 5; }
+    }
+    for (int f = sub + 8 * DEC_CACHED; f < fields; f += 8) {
+      const float x = live ? __ldg(px + f) : -INFINITY;
+      if (x > best) { best = x; best_idx = f - 5; }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {  // first index wins ties, like torch.max
+    for (int o = 4; o > 0; o >>= 1) {  // first index wins ties, like torch.max
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
       if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
     }
     float part = 0.f;
-    for (int f = lane; f < fields; f += 32) {
-      if (f >= 5) part += expf(((f == lane) ? head : __ldg(px + f)) - best);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    const float h0 = __shfl_sync(0xffffffffu, head, 0), h1 = __shfl_sync(0xffffffffu, head, 1);
-    const float h2 = __shfl_sync(0xffffffffu, head, 2), h3 = __shfl_sync(0xffffffffu, head, 3);
-    const float h4 = __shfl_sync(0xffffffffu, head, 4);
-    if (lane == b) { tx = h0; ty = h1; tw = h2; th = h3; to = h4; sum = part; cls = best_idx; }
+    for (int i = 0; i < DEC_CACHED; ++i) {
+      const int f = sub + 8 * i;
+      if (f >= 5 && f < fields) part += expf(v[i] - best);
+    }
+    for (int f = sub + 8 * DEC_CACHED; f < fields; f += 8) part += live ? expf(__ldg(px + f) - best) : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    // lane b (b = 4*it + g) takes box b's raw fields: tx..to sit in lanes 8g .. 8g+4 of v[0]
+    const int g8 = (lane & 3) * 8;
+    const float h0 = __shfl_sync(0xffffffffu, v[0], g8), h1 = __shfl_sync(0xffffffffu, v[0], g8 + 1);
+    const float h2 = __shfl_sync(0xffffffffu, v[0], g8 + 2), h3 = __shfl_sync(0xffffffffu, v[0], g8 + 3);
+    const float h4 = __shfl_sync(0xffffffffu, v[0], g8 + 4);
+    const float ps = __shfl_sync(0xffffffffu, part, g8);
+    const int pc = __shfl_sync(0xffffffffu, best_idx, g8);
+    if ((lane >> 2) == it) { tx = h0; ty = h1; tw = h2; th = h3; to = h4; sum = ps; cls = pc; }
   }
 
   // ---- phase 2: lane b finishes box b ---------------------------------------------------------
@@ -232,8 +258,8 @@ int y3_yolo_decode_dense(const y3_head_desc* d, const float* logits, float* bbox
   if (rc != Y3_OK) return rc;
   Y3_CHECK_ARG(bbox_xywh && class_prob && class_idx, "decode_dense: null output");
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(bbox_xywh) & 15) == 0, "decode_dense: bbox must be 16-byte aligned");
-  decode_dense_kernel<<<decode_grid(d), 256, 0, (cudaStream_t)stream>>>(
-      *d, logits, bbox_xywh, class_prob, reinterpret_cast<long long*>(class_idx));
+  Y3_CUDA_OK(launch_kernel(decode_dense_kernel, dim3(decode_grid(d)), dim3(256), 0, (cudaStream_t)stream, 
+      *d, logits, bbox_xywh, class_prob, reinterpret_cast<long long*>(class_idx)));
   Y3_LAUNCH_OK("decode_dense_kernel");
   return Y3_OK;
 }
@@ -246,7 +272,7 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits, float prob_
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0, "decode_cands: cands must be 16-byte aligned");
   const int per_img = d->num_anchors * d->g_h * d->g_w;
   const dim3 grid((per_img + CAND_BOXES - 1) / CAND_BOXES, d->n);
-  decode_cands_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, logits, prob_thresh, orig_hw, cands, counts, cap);
+  Y3_CUDA_OK(launch_kernel(decode_cands_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, *d, logits, prob_thresh, orig_hw, cands, counts, cap));
   Y3_LAUNCH_OK("decode_cands_kernel");
   return Y3_OK;
 }

@@ -48,7 +48,9 @@ __device__ __forceinline__ bool iou_gt(const Box4& a, const Box4& b, double thr)
 __global__ void __launch_bounds__(1024)
 nms_bucket_kernel(const y3_cand* __restrict__ cands, const int* __restrict__ counts, int cap,
                   int num_classes, int per_class, y3_cand* __restrict__ bucketed,
-                  int* __restrict__ seg_off, int* __restrict__ class_first_box) {
+                  int* __restrict__ seg_off, int* __restrict__ class_first_box,
+                  int* __restrict__ class_start) {
+  pdl_enter();
   __shared__ int hist[MAX_CLASSES];
   __shared__ int first[MAX_CLASSES];
   __shared__ int offs[MAX_CLASSES + 1];
@@ -73,7 +75,10 @@ nms_bucket_kernel(const y3_cand* __restrict__ cands, const int* __restrict__ cou
     offs[C] = run;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c <= C; c += blockDim.x) seg_off[(long long)img * (C + 1) + c] = offs[c];
+  for (int c = threadIdx.x; c <= C; c += blockDim.x) {
+    seg_off[(long long)img * (C + 1) + c] = offs[c];
+    if (class_start) class_start[(long long)img * (C + 1) + c] = offs[c];
+  }
   if (class_first_box)
     for (int c = threadIdx.x; c < C; c += blockDim.x) class_first_box[(long long)img * C + c] = first[c];
   for (int c = threadIdx.x; c < C; c += blockDim.x) hist[c] = 0;  // reuse as cursors
@@ -96,35 +101,124 @@ __device__ __forceinline__ bool before(float pa, int ba, float pb, int bb) {
 }
 
 // Segments of up to BITMASK_MAX boxes (every realistic per-class segment) take the bitmask path:
-// all threads fill the n x n/32 "i suppresses j" bit matrix in shared memory (one IoU test per
-// lane, rows reduced with __ballot_sync), then ONE warp walks the boxes in score order keeping
-// the running "removed" set as one 32-bit word per lane.  Larger segments (class-agnostic NMS
-// over thousands of boxes) use the chunked pivot scheme below.
+// keys and boxes are staged in shared memory, rank-sorted there, all threads fill the
+// n x ceil(n/32) "i suppresses j" bit matrix (one IoU test per lane, rows reduced with
+// __ballot_sync), then ONE warp resolves the greedy order 32 boxes at a time: the 32x32 diagonal
+// block is walked with a register-only dependency chain, and the rows of the chunk's KEPT boxes
+// are OR-ed into the later words of the removed set (lane w owns bits [32w, 32w+32)).
+// Larger segments (class-agnostic NMS over thousands of boxes) use the chunked pivot scheme
+// below, with the output `keep` bytes doubling as the alive flags.
 static constexpr int BITMASK_MAX = 512;
 static constexpr int BITMASK_WORDS = BITMASK_MAX / 32;
 
-__global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
-                                   int cap, int C, double thr, y3_cand* __restrict__ sorted,
-                                   uint8_t* __restrict__ keep, int alive_bytes) {
-  extern __shared__ __align__(16) uint8_t dyn_smem[];
-  uint8_t* alive = dyn_smem;                                              // [alive_bytes] (large path)
-  int4* sbox = reinterpret_cast<int4*>(dyn_smem + alive_bytes);           // [BITMASK_MAX]
-  uint32_t* smask = reinterpret_cast<uint32_t*>(sbox + BITMASK_MAX);      // [BITMASK_MAX][BITMASK_WORDS]
+__global__ void __launch_bounds__(1024)
+nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
+                   int cap, int C, double thr, y3_cand* __restrict__ sorted,
+                   uint8_t* __restrict__ keep, int* __restrict__ class_kept) {
+  pdl_enter();
+  __shared__ int4 sbox[BITMASK_MAX];
+  __shared__ float skey_p[BITMASK_MAX];
+  __shared__ int skey_b[BITMASK_MAX];
+  __shared__ uint32_t smask[BITMASK_MAX * BITMASK_WORDS];
   __shared__ uint32_t kept_mask_s;
   const int img = blockIdx.y;
   const int seg = blockIdx.x;
   const int off = seg_off[(long long)img * (C + 1) + seg];
   const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
-  if (n <= 0) return;
+  if (n <= 0) {
+    if (class_kept && threadIdx.x == 0) class_kept[(long long)img * C + seg] = 0;
+    return;
+  }
   const y3_cand* src = bucketed + (long long)img * cap + off;
   y3_cand* out = sorted + (long long)img * cap + off;
   uint8_t* keep_out = keep + (long long)img * cap + off;
-  const bool small = n <= BITMASK_MAX;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
 
-  // ---- rank sort by (prob desc, box asc) ------------------------------------------------
+  if (n <= BITMASK_MAX) {
+    // ---- rank sort by (prob desc, box asc), keys in shared memory ---------------------------
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+      skey_p[i] = __uint_as_float(hi.x);
+      skey_b[i] = (int)hi.z;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+      const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+      const float p = __uint_as_float(hi.x);
+      const int b = (int)hi.z;
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) rank += before(skey_p[j], skey_b[j], p, b) ? 1 : 0;
+      reinterpret_cast<uint4*>(out + rank)[0] = lo;
+      reinterpret_cast<uint4*>(out + rank)[1] = hi;
+      sbox[rank] = make_int4((int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w);
+    }
+    __syncthreads();
+    // ---- bit matrix: word (i, w) holds, for j = 32w + lane, [j > i and iou(i, j) > thr] ----
+    const int words = (n + 31) >> 5;
+    for (int item = warp; item < n * words; item += nwarps) {
+      const int i = item / words;
+      const int w = item - i * words;
+      if (32 * w + 31 <= i) {  // every j of this word precedes i: nothing to suppress
+        if (lane == 0) smask[item] = 0u;
+        continue;
+      }
+      const int j = 32 * w + lane;
+      bool sup = false;
+      if (j < n && j > i) {
+        const int4 bi = sbox[i], bj = sbox[j];
+        sup = iou_gt(Box4{bi.x, bi.y, bi.z, bi.w}, Box4{bj.x, bj.y, bj.z, bj.w}, thr);
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0) smask[item] = word;
+    }
+    __syncthreads();
+    // ---- greedy scan, 32 boxes per step ---------------------------------------------------------
+    if (warp == 0) {
+      uint32_t removed = 0;  // lane w: bits [32w, 32w+32) of the removed set
+      for (int c = 0; c < words; ++c) {
+        const int i0 = 32 * c;
+        const int cnt = min(32, n - i0);
+        // diagonal block: lane t holds which boxes of this chunk box i0+t suppresses
+        const uint32_t diag = (lane < cnt) ? smask[(i0 + lane) * words + c] : 0u;
+        uint32_t rem = __shfl_sync(0xffffffffu, removed, c);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const uint32_t dt = __shfl_sync(0xffffffffu, diag, t);  // independent of the chain on `rem`
+          if (!((rem >> t) & 1u)) rem |= dt;
+        }
+        if (lane == c) removed = rem;
+        uint32_t kept = ~rem & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));  // warp-uniform
+        if (lane > c && lane < words) {
+          while (kept) {
+            const int t = __ffs(kept) - 1;
+            kept &= kept - 1;
+            removed |= smask[(i0 + t) * words + lane];
+          }
+        }
+      }
+      // box i is kept iff no earlier kept box set its bit
+      int nkept = 0;
+      for (int b = 0; b < 32; ++b) {
+        const int i = 32 * lane + b;
+        if (i < n) {
+          const int k = ((removed >> b) & 1u) ? 0 : 1;
+          keep_out[i] = (uint8_t)k;
+          nkept += k;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, o);
+      if (class_kept && lane == 0) class_kept[(long long)img * C + seg] = nkept;
+    }
+    return;
+  }
+
+  // ---- large segment: rank sort straight from global memory ---------------------------------
+  volatile uint8_t* alive = keep_out;  // written and re-read by different threads of this CTA
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
     const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
@@ -137,44 +231,9 @@ __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const i
     }
     reinterpret_cast<uint4*>(out + rank)[0] = lo;
     reinterpret_cast<uint4*>(out + rank)[1] = hi;
-    if (small) sbox[rank] = make_int4((int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w);
-    else alive[i] = 1;
+    alive[i] = 1;
   }
-  __syncthreads();  // global writes to `out` by this CTA are visible to it from here on
-
-  if (small) {
-    // ---- bit matrix: word (i, w) holds, for j = 32w + lane, [j > i and iou(i, j) > thr] ----
-    const int words = (n + 31) >> 5;
-    for (int item = warp; item < n * words; item += nwarps) {
-      const int i = item / words;
-      const int w = item - i * words;
-      if (32 * w + 31 <= i) {  // every j of this word precedes i: nothing to suppress
-        if (lane == 0) smask[i * BITMASK_WORDS + w] = 0u;
-        continue;
-      }
-      const int j = 32 * w + lane;
-      bool sup = false;
-      if (j < n && j > i) {
-        const int4 bi = sbox[i], bj = sbox[j];
-        sup = iou_gt(Box4{bi.x, bi.y, bi.z, bi.w}, Box4{bj.x, bj.y, bj.z, bj.w}, thr);
-      }
-      const uint32_t word = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0) smask[i * BITMASK_WORDS + w] = word;
-    }
-    __syncthreads();
-    // ---- greedy scan: lane w owns bits [32w, 32w+32) of the removed set ---------------------
-    if (warp == 0) {
-      uint32_t removed = 0;
-      for (int i = 0; i < n; ++i) {
-        const uint32_t row = (lane < words) ? smask[i * BITMASK_WORDS + lane] : 0u;  // independent of `removed`
-        const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
-        const bool kept = ((r >> (i & 31)) & 1u) == 0;
-        if (kept) removed |= row;
-        if (lane == 0) keep_out[i] = kept ? 1 : 0;
-      }
-    }
-    return;
-  }
+  __syncthreads();  // global writes to `out` / `alive` by this CTA are visible to it from here on
 
   // ---- large segment: greedy suppression, 32 pivots at a time ----------------------------
   for (int c0 = 0; c0 < n; c0 += 32) {
@@ -228,6 +287,56 @@ __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const i
     }
     __syncthreads();
   }
+  if (class_kept) {
+    if (threadIdx.x == 0) kept_mask_s = 0u;
+    __syncthreads();
+    int local = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) local += alive[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(&kept_mask_s, (uint32_t)local);
+    __syncthreads();
+    if (threadIdx.x == 0) class_kept[(long long)img * C + seg] = (int)kept_mask_s;
+  }
+}
+
+// a17: the three arrays `inference` returns per image (yolov3/inference.py:360-366), written
+// straight in their final dtypes and final order: one warp per (image, class) segment compacts
+// the segment's kept records (already prob-descending) to dst_off[image, class], the position the
+// host assigned to that class group (class groups follow the reference's set() visiting order).
+__global__ void __launch_bounds__(128)
+emit_detections_kernel(const y3_cand* __restrict__ sorted, const uint8_t* __restrict__ keep,
+                       const int* __restrict__ class_start, const int* __restrict__ dst_off, int n_images,
+                       int cap, int C, long long* __restrict__ tlbr, float* __restrict__ prob,
+                       long long* __restrict__ cls) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)n_images * C) return;
+  const int img = (int)(wid / C);
+  const int c = (int)(wid - (long long)img * C);
+  const int off = class_start[(long long)img * (C + 1) + c];
+  const int n = class_start[(long long)img * (C + 1) + c + 1] - off;
+  long long dst = dst_off[wid];
+  if (n <= 0 || dst < 0) return;
+  const y3_cand* src = sorted + (long long)img * cap + off;
+  const uint8_t* kp = keep + (long long)img * cap + off;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool k = i < n && kp[i] != 0;
+    const uint32_t ball = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const long long o = dst + __popc(ball & ((1u << lane) - 1u));
+      const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+      const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+      longlong2* t = reinterpret_cast<longlong2*>(tlbr + 4 * o);
+      t[0] = make_longlong2((long long)(int)lo.x, (long long)(int)lo.y);
+      t[1] = make_longlong2((long long)(int)lo.z, (long long)(int)lo.w);
+      prob[o] = __uint_as_float(hi.x);
+      cls[o] = (long long)(int)hi.y;
+    }
+    dst += __popc(ball);
+  }
 }
 
 // Ordered compaction of kept records per image; dets are written image after image into one
@@ -235,6 +344,7 @@ __global__ void nms_segment_kernel(const y3_cand* __restrict__ bucketed, const i
 __global__ void __launch_bounds__(1024)
 nms_count_kernel(const uint8_t* __restrict__ keep, const int* __restrict__ counts, int cap,
                  int* __restrict__ det_counts) {
+  pdl_enter();
   __shared__ int total;
   const int img = blockIdx.x;
   int n = counts[img];
@@ -254,6 +364,7 @@ __global__ void __launch_bounds__(1024)
 nms_compact_kernel(const y3_cand* __restrict__ sorted, const uint8_t* __restrict__ keep,
                    const int* __restrict__ counts, int cap, y3_cand* __restrict__ dets,
                    const int* __restrict__ det_counts, int n_images, int flat) {
+  pdl_enter();
   __shared__ int warp_sums[32];
   __shared__ int base_s;
   const int img = blockIdx.x;
@@ -304,12 +415,11 @@ size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes) {
 
 int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, int32_t num_classes,
            double iou_thresh, int32_t per_class, y3_cand* sorted, uint8_t* keep, int32_t* class_first_box,
-           void* workspace, size_t workspace_bytes, void* stream) {
+           int32_t* class_start, int32_t* class_kept, void* workspace, size_t workspace_bytes, void* stream) {
   Y3_CHECK_ARG(cands && counts && sorted && keep && workspace, "nms: null argument");
   Y3_CHECK_ARG(n > 0 && cap > 0, "nms: bad n=%d cap=%d", n, cap);
   Y3_CHECK_ARG(num_classes > 0 && num_classes <= MAX_CLASSES, "nms: num_classes=%d out of range (1..%d)",
                num_classes, MAX_CLASSES);
-  Y3_CHECK_ARG(cap <= 200 * 1024, "nms: cap=%d exceeds the shared-memory flag array (204800)", cap);
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0 && (reinterpret_cast<uintptr_t>(sorted) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "nms: buffers must be 16-byte aligned");
   if (workspace_bytes < y3_nms_workspace_bytes(n, cap, num_classes)) {
@@ -322,23 +432,30 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
   y3_cand* bucketed = reinterpret_cast<y3_cand*>(workspace);
   int* seg_off = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)n * cap * sizeof(y3_cand));
 
-  nms_bucket_kernel<<<n, 1024, 0, s>>>(cands, counts, cap, num_classes, per_class, bucketed, seg_off,
-                                       class_first_box);
+  Y3_CUDA_OK(launch_kernel(nms_bucket_kernel, dim3(n), dim3(1024), 0, s, cands, counts, cap, num_classes, per_class, bucketed, seg_off,
+                           class_first_box, class_start));
   Y3_LAUNCH_OK("nms_bucket_kernel");
 
-  // dynamic smem: alive[] (one byte per box of the largest possible segment = cap, large path)
-  // + boxes and bit matrix of the bitmask path
-  const int alive_bytes = (int)(((size_t)cap + 15) / 16 * 16);
-  const size_t smem = (size_t)alive_bytes + BITMASK_MAX * sizeof(int4) + (size_t)BITMASK_MAX * BITMASK_WORDS * 4;
-  static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    Y3_CUDA_OK(cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
-  const int threads = per_class ? 256 : 1024;
-  nms_segment_kernel<<<dim3(C, n), threads, smem, s>>>(bucketed, seg_off, cap, C, iou_thresh, sorted, keep,
-                                                       alive_bytes);
+  const int threads = per_class ? 256 : 1024;  // one huge segment per image: more threads per CTA
+  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(dim3(C, n)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh, sorted, keep,
+                           class_kept));
   Y3_LAUNCH_OK("nms_segment_kernel");
+  return Y3_OK;
+}
+
+int y3_emit_detections(const y3_cand* sorted, const uint8_t* keep, const int32_t* class_start,
+                       const int32_t* dst_off, int32_t n, int32_t cap, int32_t num_segments, int64_t* tlbr,
+                       float* prob, int64_t* cls, void* stream) {
+  Y3_CHECK_ARG(sorted && keep && class_start && dst_off && tlbr && prob && cls, "emit_detections: null argument");
+  Y3_CHECK_ARG(n > 0 && cap > 0 && num_segments > 0, "emit_detections: bad n=%d cap=%d segments=%d", n, cap,
+               num_segments);
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(tlbr) & 15) == 0, "emit_detections: tlbr must be 16-byte aligned");
+  const long long warps = (long long)n * num_segments;
+  const int grid = (int)((warps + 3) / 4);
+  Y3_CUDA_OK(launch_kernel(emit_detections_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, sorted, keep,
+                           class_start, dst_off, n, cap, num_segments, reinterpret_cast<long long*>(tlbr), prob,
+                           reinterpret_cast<long long*>(cls)));
+  Y3_LAUNCH_OK("emit_detections_kernel");
   return Y3_OK;
 }
 
@@ -347,9 +464,9 @@ int y3_compact_kept(const y3_cand* sorted, const uint8_t* keep, const int32_t* c
   Y3_CHECK_ARG(sorted && keep && counts && dets && det_counts, "compact_kept: null argument");
   Y3_CHECK_ARG(n > 0 && cap > 0, "compact_kept: bad n=%d cap=%d", n, cap);
   cudaStream_t s = (cudaStream_t)stream;
-  nms_count_kernel<<<n, 1024, 0, s>>>(keep, counts, cap, det_counts);
+  Y3_CUDA_OK(launch_kernel(nms_count_kernel, dim3(n), dim3(1024), 0, s, keep, counts, cap, det_counts));
   Y3_LAUNCH_OK("nms_count_kernel");
-  nms_compact_kernel<<<n, 1024, 0, s>>>(sorted, keep, counts, cap, dets, det_counts, n, flat);
+  Y3_CUDA_OK(launch_kernel(nms_compact_kernel, dim3(n), dim3(1024), 0, s, sorted, keep, counts, cap, dets, det_counts, n, flat));
   Y3_LAUNCH_OK("nms_compact_kernel");
   return Y3_OK;
 }

@@ -20,6 +20,7 @@ static inline int grid_for(long long work_items, int block) {
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                int n, int h, int w, int cvec, int ld_x, int ld_y, int k, int stride,
                                int ho, int wo, int zero_pad) {
+  pdl_enter();
   const long long total = (long long)n * ho * wo * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -54,6 +55,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 __global__ void spp3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y5,
                             __nv_bfloat16* __restrict__ y9, __nv_bfloat16* __restrict__ y13, int n,
                             int h, int w, int cvec, int ld_x, int ld_y) {
+  pdl_enter();
   const long long total = (long long)n * h * w * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -93,6 +95,7 @@ __global__ void spp3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ y, long long pixels, int cvec, int ld_a,
                            int ld_b, int ld_y) {
+  pdl_enter();
   const long long total = pixels * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -114,6 +117,7 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 // ---- route / torch.cat slice copy (yolov3/darknet.py:369-375), unfused form --------------
 __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                      long long pixels, int cvec, int ld_x, int ld_y) {
+  pdl_enter();
   const long long total = pixels * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -126,6 +130,7 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // ---- nn.Upsample(scale 2, nearest) (yolov3/darknet.py:299-305), unfused form --------------
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                   int n, int h, int w, int cvec, int ld_x, int ld_y) {
+  pdl_enter();
   const int ho = 2 * h, wo = 2 * w;
   const long long total = (long long)n * ho * wo * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -145,6 +150,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 // float32 NCHW -> NHWC bf16, channels zero-padded to c_pad (multiple of 8).
 __global__ void pack_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                      int c, int hw, int c_pad) {
+  pdl_enter();
   const long long total = (long long)n * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -165,6 +171,7 @@ __global__ void pack_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16*
 // uint8 BGR HWC -> RGB, fp32 divide by 255 (yolov3/inference.py:332-333), bf16 NHWC padded.
 __global__ void pack_bgr_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    long long pixels, int c_pad) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels;
        i += (long long)gridDim.x * blockDim.x) {
     const uint8_t* src = x + i * 3;
@@ -208,6 +215,7 @@ __device__ __forceinline__ void im2col3x3_pixel(Load load, int h, int w, int y, 
 template <int C>
 __global__ void im2col3x3_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                           int h, int w, int k_pad) {
+  pdl_enter();
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -222,6 +230,7 @@ __global__ void im2col3x3_nchw_f32_kernel(const float* __restrict__ x, __nv_bflo
 
 __global__ void im2col3x3_bgr_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
                                         int w, int k_pad) {
+  pdl_enter();
   const long long total = (long long)n * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -262,8 +271,8 @@ int y3_maxpool(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t 
     wo = (w - ksize) / stride + 1;
   }
   const long long work = (long long)n * ho * wo * (c / 8);
-  maxpool_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c / 8, ld_x, ld_y, ksize, stride, ho, wo, zero_pad);
+  Y3_CUDA_OK(launch_kernel(maxpool_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c / 8, ld_x, ld_y, ksize, stride, ho, wo, zero_pad));
   Y3_LAUNCH_OK("maxpool_kernel");
   return Y3_OK;
 }
@@ -275,8 +284,8 @@ int y3_spp3(const void* x, void* y5, void* y9, void* y13, int32_t n, int32_t h, 
   Y3_CHECK_ARG(ld_x >= c && ld_y >= c && ld_x % 8 == 0 && ld_y % 8 == 0, "spp3: bad pitch");
   Y3_CHECK_ARG(aligned16(x) && aligned16(y5) && aligned16(y9) && aligned16(y13), "spp3: alignment");
   const long long work = (long long)n * h * w * (c / 8);
-  spp3_kernel<<<grid_for(work, 128), 128, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y5, (__nv_bfloat16*)y9, (__nv_bfloat16*)y13, n, h, w, c / 8, ld_x, ld_y);
+  Y3_CUDA_OK(launch_kernel(spp3_kernel, dim3(grid_for(work, 128)), dim3(128), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y5, (__nv_bfloat16*)y9, (__nv_bfloat16*)y13, n, h, w, c / 8, ld_x, ld_y));
   Y3_LAUNCH_OK("spp3_kernel");
   return Y3_OK;
 }
@@ -287,8 +296,8 @@ int y3_add(const void* a, const void* b, void* y, int64_t pixels, int32_t c, int
   Y3_CHECK_ARG(pixels > 0 && c > 0 && c % 8 == 0, "add: bad shape");
   Y3_CHECK_ARG(ld_a >= c && ld_b >= c && ld_y >= c && ld_a % 8 == 0 && ld_b % 8 == 0 && ld_y % 8 == 0, "add: bad pitch");
   Y3_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(y), "add: alignment");
-  add_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, pixels, c / 8, ld_a, ld_b, ld_y);
+  Y3_CUDA_OK(launch_kernel(add_kernel, dim3(grid_for(pixels * (c / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, pixels, c / 8, ld_a, ld_b, ld_y));
   Y3_LAUNCH_OK("add_kernel");
   return Y3_OK;
 }
@@ -298,8 +307,8 @@ int y3_copy_channels(const void* x, void* y, int64_t pixels, int32_t c, int32_t 
   Y3_CHECK_ARG(pixels > 0 && c > 0 && c % 8 == 0, "copy_channels: bad shape");
   Y3_CHECK_ARG(ld_x >= c && ld_y >= c && ld_x % 8 == 0 && ld_y % 8 == 0, "copy_channels: bad pitch");
   Y3_CHECK_ARG(aligned16(x) && aligned16(y), "copy_channels: alignment");
-  copy_channels_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, c / 8, ld_x, ld_y);
+  Y3_CUDA_OK(launch_kernel(copy_channels_kernel, dim3(grid_for(pixels * (c / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, c / 8, ld_x, ld_y));
   Y3_LAUNCH_OK("copy_channels_kernel");
   return Y3_OK;
 }
@@ -311,8 +320,8 @@ int y3_upsample2x(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32
   Y3_CHECK_ARG(ld_x >= c && ld_y >= c && ld_x % 8 == 0 && ld_y % 8 == 0, "upsample2x: bad pitch");
   Y3_CHECK_ARG(aligned16(x) && aligned16(y), "upsample2x: alignment");
   const long long work = (long long)n * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c / 8, ld_x, ld_y);
+  Y3_CUDA_OK(launch_kernel(upsample2x_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c / 8, ld_x, ld_y));
   Y3_LAUNCH_OK("upsample2x_kernel");
   return Y3_OK;
 }
@@ -323,8 +332,8 @@ int y3_pack_nchw_f32(const float* x, void* y, int32_t n, int32_t c, int32_t h, i
   Y3_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c && c_pad % 8 == 0, "pack_nchw_f32: bad shape");
   Y3_CHECK_ARG(aligned16(y), "pack_nchw_f32: alignment");
   const long long work = (long long)n * h * w;
-  pack_nchw_f32_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, (__nv_bfloat16*)y, n, c, h * w, c_pad);
+  Y3_CUDA_OK(launch_kernel(pack_nchw_f32_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      x, (__nv_bfloat16*)y, n, c, h * w, c_pad));
   Y3_LAUNCH_OK("pack_nchw_f32_kernel");
   return Y3_OK;
 }
@@ -334,7 +343,7 @@ int y3_pack_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h, int32_t w, i
   Y3_CHECK_ARG(n > 0 && h > 0 && w > 0 && c_pad >= 8 && c_pad % 8 == 0, "pack_bgr_u8: bad shape");
   Y3_CHECK_ARG(aligned16(y), "pack_bgr_u8: alignment");
   const long long work = (long long)n * h * w;
-  pack_bgr_u8_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, work, c_pad);
+  Y3_CUDA_OK(launch_kernel(pack_bgr_u8_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, work, c_pad));
   Y3_LAUNCH_OK("pack_bgr_u8_kernel");
   return Y3_OK;
 }
@@ -348,9 +357,9 @@ int y3_im2col3x3_nchw_f32(const float* x, void* y, int32_t n, int32_t c, int32_t
   const long long work = (long long)n * h * w;
   const int grid = grid_for(work, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c == 3) im2col3x3_nchw_f32_kernel<3><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
-  else if (c == 2) im2col3x3_nchw_f32_kernel<2><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
-  else im2col3x3_nchw_f32_kernel<1><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)y, n, h, w, k_pad);
+  if (c == 3) Y3_CUDA_OK(launch_kernel(im2col3x3_nchw_f32_kernel<3>, dim3(grid), dim3(256), 0, st, x, (__nv_bfloat16*)y, n, h, w, k_pad));
+  else if (c == 2) Y3_CUDA_OK(launch_kernel(im2col3x3_nchw_f32_kernel<2>, dim3(grid), dim3(256), 0, st, x, (__nv_bfloat16*)y, n, h, w, k_pad));
+  else Y3_CUDA_OK(launch_kernel(im2col3x3_nchw_f32_kernel<1>, dim3(grid), dim3(256), 0, st, x, (__nv_bfloat16*)y, n, h, w, k_pad));
   Y3_LAUNCH_OK("im2col3x3_nchw_f32_kernel");
   return Y3_OK;
 }
@@ -360,8 +369,8 @@ int y3_im2col3x3_bgr_u8(const uint8_t* x, void* y, int32_t n, int32_t h, int32_t
   Y3_CHECK_ARG(n > 0 && h > 0 && w > 0 && k_pad == 32, "im2col3x3_bgr_u8: k_pad must be 32");
   Y3_CHECK_ARG(aligned16(y), "im2col3x3_bgr_u8: alignment");
   const long long work = (long long)n * h * w;
-  im2col3x3_bgr_u8_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, h, w,
-                                                                                  k_pad);
+  Y3_CUDA_OK(launch_kernel(im2col3x3_bgr_u8_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n, h, w,
+                                                                                  k_pad));
   Y3_LAUNCH_OK("im2col3x3_bgr_u8_kernel");
   return Y3_OK;
 }

@@ -21,10 +21,10 @@ EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
     "y3_conv2d", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
-    "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept",
+    "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
 )
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ConvDesc(ctypes.Structure):
@@ -78,7 +78,8 @@ def lib():
     L.y3_nms_workspace_bytes.argtypes = [c_int32] * 3
     L.y3_nms_workspace_bytes.restype = c_size_t
     L.y3_nms.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_void_p, c_void_p,
-                         c_void_p, c_void_p, c_size_t, c_void_p]
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.y3_emit_detections.argtypes = [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 4
     L.y3_compact_kept.argtypes = [c_void_p] * 3 + [c_int32] * 2 + [c_void_p] * 2 + [c_int32, c_void_p]
     if L.y3_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libyolov3_b200.so ABI {L.y3_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -207,10 +208,16 @@ def nms_workspace_bytes(n, cap, num_classes):
     return int(lib().y3_nms_workspace_bytes(n, cap, num_classes))
 
 
-def nms(cands, counts, n, cap, num_classes, iou_thresh, per_class, sorted_out, keep, class_first_box, workspace):
+def nms(cands, counts, n, cap, num_classes, iou_thresh, per_class, sorted_out, keep, class_first_box, workspace,
+        class_start=None, class_kept=None):
     _check(lib().y3_nms(_ptr(cands), _ptr(counts), n, cap, num_classes, float(iou_thresh), int(per_class),
-                        _ptr(sorted_out), _ptr(keep), _ptr(class_first_box), _ptr(workspace),
-                        workspace.numel() * workspace.element_size(), _stream()))
+                        _ptr(sorted_out), _ptr(keep), _ptr(class_first_box), _ptr(class_start), _ptr(class_kept),
+                        _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()))
+
+
+def emit_detections(sorted_in, keep, class_start, dst_off, n, cap, num_segments, tlbr, prob, cls):
+    _check(lib().y3_emit_detections(_ptr(sorted_in), _ptr(keep), _ptr(class_start), _ptr(dst_off), n, cap,
+                                    num_segments, _ptr(tlbr), _ptr(prob), _ptr(cls), _stream()))
 
 
 def compact_kept(sorted_in, keep, counts, n, cap, dets, det_counts, flat):

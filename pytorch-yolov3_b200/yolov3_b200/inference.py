@@ -6,14 +6,14 @@ nrsyed/pytorch-yolov3 (``inference`` :286-368, ``non_max_suppression`` :220-266,
 Everything between the uint8 images and the kept detections runs on the GPU in one CUDA-graph
 replay: BGR->RGB /255 packing, the Darknet forward, YOLO decode + threshold + pixel scaling +
 integer truncation + tl/br conversion, per-class NMS and compaction.  The host copies the
-images up (pinned memory), copies the kept records down, and re-orders class groups the way the
-reference's ``set(class_idx)`` loop visits them.  There is no CPU implementation here.
+images up (pinned memory), reads back how many detections every (image, class) group kept, tells
+the device where each group goes (class groups follow the reference's ``set(class_idx)`` visiting
+order) and receives the final int64 / float32 arrays.  There is no CPU implementation here.
 """
 import numpy as np
 import torch
 
 from . import _lib
-from .engine import records_to_numpy
 
 
 def cxywh_to_tlbr(bbox_xywh):
@@ -28,14 +28,43 @@ def cxywh_to_tlbr(bbox_xywh):
     return bbox_tlbr
 
 
+_INT32_MAX = np.iinfo(np.int32).max
+
+
 def _set_order(first_box_row):
     """Classes in the order the reference's ``for class_ in set(class_idx)`` loop visits them
     (yolov3/inference.py:247-250).  A Python set's iteration order depends only on the hashes and
     on the order in which DISTINCT keys were inserted, i.e. on each class's first occurrence in
-    candidate order — which is ascending box index, recorded on the device by ``y3_nms``."""
-    present = np.nonzero(first_box_row != np.iinfo(np.int32).max)[0]
+    candidate order — which is ascending box index, recorded on the device by ``y3_nms``.
+
+    CPython fact used as a fast path (checked by tests/test_host_logic.py against real sets): with
+    at least 19 distinct keys, all of them small non-negative ints below 128, the table has at
+    least 128 slots, every key sits in slot ``key`` and iteration is ascending."""
+    present = np.nonzero(first_box_row != _INT32_MAX)[0]
+    if present.size >= 19 and present[-1] < 128:
+        return present.astype(np.int64)
     by_first_seen = present[np.argsort(first_box_row[present], kind="stable")]
-    return list(set(np.int64(c) for c in by_first_seen))
+    return np.fromiter(set(np.int64(c) for c in by_first_seen), dtype=np.int64, count=present.size)
+
+
+def _destinations(class_kept, first_box):
+    """Where every (image, class) group of kept detections goes in the flat, image-after-image
+    output: class groups of one image in the reference's ``set()`` visiting order.  Returns
+    (dst_off int32 [B,C], kept per image int64 [B])."""
+    B, C = class_kept.shape
+    kept64 = class_kept.astype(np.int64)
+    per_image = kept64.sum(axis=1)
+    flat = kept64.ravel()
+    dst = (np.cumsum(flat) - flat).reshape(B, C)  # ascending class order everywhere ...
+    n_present = (first_box != _INT32_MAX).sum(axis=1)
+    ascending_ok = (n_present >= 19) & (C <= 128)
+    if not ascending_ok.all():  # ... except where the set order is not ascending
+        base = np.cumsum(per_image) - per_image
+        for i in np.nonzero(~ascending_ok)[0]:
+            order = _set_order(first_box[i])
+            k = kept64[i, order]
+            dst[i, order] = base[i] + np.cumsum(k) - k
+    return dst.astype(np.int32), per_image
 
 
 def _order_like_reference(cls_sorted, first_box_row):
@@ -76,7 +105,7 @@ def _stack_into(dst, images):
     if _copy_pool is None:
         import os
         from concurrent.futures import ThreadPoolExecutor
-        _copy_pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+        _copy_pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
     workers = _copy_pool._max_workers
 
     def job(lo):
@@ -117,38 +146,46 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
     if eng.device != dev:
         raise RuntimeError(f"net runs on {eng.device}, inference(device='{device}') requested")
 
+    C = eng.num_classes
     with torch.cuda.device(dev):
         io = eng.__dict__.setdefault("_host_io", {})
         if not io:
             io["img"] = _pinned((B, H, W, 3), torch.uint8)
             io["hw"] = _pinned((B, 2), torch.int32)
-            io["counts"] = _pinned((B,), torch.int32)
-            io["first"] = _pinned((B, eng.num_classes), torch.int32)
-            io["dets"] = _pinned((B * eng.cap, 8), torch.int32)
+            io["meta"] = _pinned((2, B, C), torch.int32)
+            io["dst"] = _pinned((B, C), torch.int32)
+        stream = torch.cuda.current_stream()
         _stack_into(io["img"].numpy(), images)  # raises ValueError on ragged shapes, like np.stack
         io["hw"].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
         eng.in_u8.copy_(io["img"], non_blocking=True)
         eng.orig_hw.copy_(io["hw"], non_blocking=True)
-        dets, det_counts, first_box = eng.detect(prob_thresh, nms_iou_thresh, "det_u8")
-        io["counts"].copy_(det_counts, non_blocking=True)
-        io["first"].copy_(first_box, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        counts = io["counts"].numpy().astype(np.int64)
-        total = int(counts.sum())
-        if total:
-            io["dets"][:total].copy_(dets[:total], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        rec = io["dets"].numpy()[:total]
-        first = io["first"].numpy()
-
-    tlbr_all, prob_all, cls_all, _ = records_to_numpy(rec)  # one conversion for the whole batch
+        eng.launch(("nms_u8", float(prob_thresh), float(nms_iou_thresh)))
+        io["meta"].copy_(eng.seg_meta, non_blocking=True)  # kept per (image, class) + first box per class
+        stream.synchronize()
+        meta = io["meta"].numpy()
+        dst_off, per_image = _destinations(meta[0], meta[1])
+        total = int(per_image.sum())
+        # results live in fresh pinned arrays (torch's caching host allocator recycles them once the
+        # caller drops the result), so the device writes the final dtypes and nothing is re-copied
+        if total == 0:
+            return [[np.zeros((0, 4), np.int64), np.zeros(0, np.float32), np.zeros(0, np.int64)] for _ in range(B)]
+        tlbr = _pinned((total, 4), torch.int64)
+        prob = _pinned((total,), torch.float32)
+        cls = _pinned((total,), torch.int64)
+        if True:
+            io["dst"].numpy()[...] = dst_off
+            eng.dst_off.copy_(io["dst"], non_blocking=True)
+            eng.emit()
+            tlbr.copy_(eng.out_tlbr[:total], non_blocking=True)
+            prob.copy_(eng.out_prob[:total], non_blocking=True)
+            cls.copy_(eng.out_cls[:total], non_blocking=True)
+            stream.synchronize()
+    tlbr, prob, cls = tlbr.numpy(), prob.numpy(), cls.numpy()
+    ends = np.cumsum(per_image).tolist()
     results, pos = [], 0
-    for i in range(B):
-        k = int(counts[i])
-        cls = cls_all[pos:pos + k]
-        perm = _order_like_reference(cls, first[i])
-        results.append([tlbr_all[pos:pos + k][perm, :], prob_all[pos:pos + k][perm], cls[perm]])
-        pos += k
+    for e in ends:
+        results.append([tlbr[pos:e], prob[pos:e], cls[pos:e]])
+        pos = e
     return results
 
 

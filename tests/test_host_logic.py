@@ -12,7 +12,7 @@ import torch
 import yolov3_b200
 from yolov3_b200 import _lib
 from yolov3_b200.engine import Engine
-from yolov3_b200.inference import _order_like_reference, _set_order
+from yolov3_b200.inference import _destinations, _order_like_reference, _set_order
 from conftest import GOLDEN, MODELS, PKG, ROOT
 
 
@@ -133,7 +133,7 @@ def test_reference_class_visiting_order_is_reproduced():
         first = np.full(max(classes, 1), np.iinfo(np.int32).max, dtype=np.int32)
         for pos, c in enumerate(cls):
             first[c] = min(first[c], pos)
-        assert _set_order(first) == list(set(cls))  # the reference's loop order (inference.py:247-250)
+        assert list(_set_order(first)) == list(set(cls))  # the reference's loop order (inference.py:247-250)
         # full permutation: records sorted (class asc, prob desc) -> reference order
         prob = rng.permutation(n).astype(np.float32)
         order = np.lexsort((-prob, cls))
@@ -145,6 +145,32 @@ def test_reference_class_visiting_order_is_reproduced():
         assert order[perm].tolist() == want
 
 
+def test_destinations_follow_the_set_order_of_every_image():
+    """`inference` tells the device where each (image, class) group of kept detections goes; the
+    layout must be image after image, class groups in the reference's set() order (ascending fast
+    path for >= 19 present classes, real set emulation below that)."""
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        B, C = int(rng.integers(1, 9)), int(rng.choice([3, 20, 80, 200]))
+        kept = np.zeros((B, C), np.int32)
+        first = np.full((B, C), np.iinfo(np.int32).max, np.int32)
+        want = np.full((B, C), -1, np.int64)
+        pos = 0
+        for i in range(B):
+            n = int(rng.integers(0, 300))
+            cls = rng.integers(0, int(rng.integers(1, C + 1)), n).astype(np.int64)
+            for j, c in enumerate(cls):
+                first[i, c] = min(first[i, c], j)
+            for c in set(cls):  # the reference's loop (inference.py:247-250)
+                kept[i, c] = int(rng.integers(1, 1 + (cls == c).sum()))
+                want[i, c] = pos
+                pos += kept[i, c]
+        dst, per_image = _destinations(kept, first)
+        assert per_image.tolist() == kept.sum(1).tolist()
+        present = kept > 0
+        assert np.array_equal(dst[present], want[present])
+
+
 def test_library_loads_and_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "yolov3_b200.h")).read()
     declared = set(re.findall(r"\b(y3_[a-z0-9_]+)\s*\(", header))
@@ -152,7 +178,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.y3_abi_version() == 1
+    assert lib.y3_abi_version() == _lib.ABI_VERSION == 2
     lib.y3_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.y3_last_error(), bytes)
 
