@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 2
+#define Y3_ABI_VERSION 3
 
 enum {
   Y3_OK = 0,
@@ -87,6 +87,38 @@ typedef struct y3_conv_desc {
 
 int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w,
               const float* bias, const void* residual, void* y, void* stream);
+
+/* ---- a5 (+a8, a12): two chained convolutional blocks, intermediate kept on chip ---------- */
+/*
+ * The first layers of Darknet-53 are memory-bound, so two block shapes run as ONE
+ * kernel each (conv_chain.cu) and their intermediate activation never reaches HBM:
+ *
+ *  y3_conv_chain_stem_u8: uint8 BGR HWC images [N,H,W,3] -> RGB /255 (yolov3/inference.py:332-333)
+ *    -> conv 3x3 / stride 1 / pad 1, 3 -> 32 (+BN folded, leaky)  -> conv 3x3 / stride 2 / pad 1,
+ *    32 -> 64 (+BN folded, leaky): blocks 0 and 1 of models/yolov3.cfg / yolov3-spp.cfg
+ *    (built at yolov3/darknet.py:244-257).  w1: bf16 [32][32] = the 27 taps in (r,s,rgb) order
+ *    padded to 32; w2: bf16 [64][3][3][32].  y: NHWC bf16 [N,H/2,W/2,64] pitch ld_y.
+ *    H/2 must be a multiple of 16 and W/2 a multiple of 8.
+ *
+ *  y3_conv_chain_res64: one residual unit x -> conv 1x1 64 -> 32 -> conv 3x3 / 1 / pad 1 32 -> 64,
+ *    + x (the [shortcut] of yolov3/darknet.py:376-379).  x: NHWC bf16 [N,H,W,64] pitch ld_x;
+ *    w1: bf16 [32][64]; w2: bf16 [64][3][3][32]; y: NHWC bf16 [N,H,W,64] pitch ld_y, y != x.
+ *    H must be a multiple of 16 and W a multiple of 8.
+ *
+ * The intermediate is rounded to bf16 exactly as the unfused y3_conv2d sequence stores it.
+ */
+typedef struct y3_chain_desc {
+  int32_t n, h, w;          /* input batch / height / width                */
+  int32_t ld_x, ld_y;       /* pixel pitches in elements (ld_x: RES only)  */
+  int32_t leaky1, leaky2;   /* LeakyReLU(0.1) after the first / second conv */
+} y3_chain_desc;
+
+int y3_conv_chain_stem_u8(const y3_chain_desc* d, const uint8_t* img, const void* w1,
+                          const float* b1, const void* w2, const float* b2, void* y,
+                          void* stream);
+int y3_conv_chain_res64(const y3_chain_desc* d, const void* x, const void* w1,
+                        const float* b1, const void* w2, const float* b2, void* y,
+                        void* stream);
 
 /* ---- a6: max-pool -------------------------------------------------------- */
 /*

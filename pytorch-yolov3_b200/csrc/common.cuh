@@ -44,6 +44,11 @@ void count_launch(int n = 1);
     y3::count_launch();                                                       \
   } while (0)
 
+// Tiled (non-im2col) bf16 tensor map of rank 2..5 (conv_umma.cu).  `map` is a 64B-aligned CUtensorMap;
+// strides_bytes has rank-1 entries (dimension 0 is dense); swizzle_bytes is 128, 64 or 32.
+int encode_tiled_map(void* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes);
+
 int num_sms();  // SM count of the current device (cached per device)
 bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 turns it off)
 

@@ -478,6 +478,27 @@ static int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_
   return Y3_OK;
 }
 
+int encode_tiled_map(void* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  int rc = resolve_driver_entry_points();
+  if (rc != Y3_OK) return rc;
+  Y3_CHECK_ARG(rank >= 2 && rank <= 5, "tensor map rank %d", rank);
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                              const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_for(swizzle_bytes / 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank %d) failed (CUresult %d): dims0=%llu box0=%u stride0=%llu", rank, (int)r,
+              (unsigned long long)dims[0], box[0], (unsigned long long)strides_bytes[0]);
+    return Y3_ECUDA;
+  }
+  return Y3_OK;
+}
+
 static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x, int block_k) {
   cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
   const uint64_t pix = (uint64_t)d->ld_x * 2;

@@ -94,6 +94,27 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 4-D tiled load over an NHWC tensor, coordinates (c, w, h, n); out-of-range elements are zero-filled
+// (negative coordinates allowed) — used to fetch a spatial patch with its halo in one request.
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c,
+                                            int32_t w, int32_t h, int32_t n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+// 4-D tiled store of a (c, w, h, n) box (elements outside the tensor are clipped).
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int32_t c, int32_t w,
+                                             int32_t h, int32_t n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
+// named barrier over `count` threads (a multiple of 32); id 0 is __syncthreads' own
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 // 4-D im2col load over an NHWC tensor: (c, w, h, n) is the first base pixel in
 // INPUT coordinates (output pixel * stride - pad), (off_w, off_h) the filter tap.
 template <int CG = 1>

@@ -19,12 +19,12 @@ LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
 # Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
 EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
-    "y3_conv2d", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
+    "y3_conv2d", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
 )
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ConvDesc(ctypes.Structure):
@@ -32,6 +32,11 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "n", "h", "w", "cin", "cout", "ksize", "stride", "pad", "ld_x", "ld_y", "ld_res",
         "leaky", "out_f32", "upsample2x", "flags")]
+
+
+class ChainDesc(ctypes.Structure):
+    """``y3_chain_desc``."""
+    _fields_ = [(n, c_int32) for n in ("n", "h", "w", "ld_x", "ld_y", "leaky1", "leaky2")]
 
 
 class HeadDesc(ctypes.Structure):
@@ -63,6 +68,8 @@ def lib():
     L.y3_launch_count.restype = c_longlong
     L.y3_reset_launch_count.restype = None
     L.y3_conv2d.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.y3_conv_chain_stem_u8.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
+    L.y3_conv_chain_res64.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
     L.y3_maxpool.argtypes = [c_void_p, c_void_p] + [c_int32] * 8 + [c_void_p]
     L.y3_spp3.argtypes = [c_void_p] * 4 + [c_int32] * 6 + [c_void_p]
     L.y3_add.argtypes = [c_void_p] * 3 + [c_int64] + [c_int32] * 4 + [c_void_p]
@@ -138,6 +145,22 @@ def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, 
     d = ConvDesc(n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, ld_res, int(leaky), int(out_f32),
                  int(upsample2x), (1 if force_im2col else 0) | (2 if force_direct else 0) | (4 if force_1cta else 0))
     _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
+
+
+def conv_chain_stem_u8(img, w1, b1, w2, b2, y_ptr, *, ld_y, leaky1=True, leaky2=True):
+    """uint8 BGR images [N,H,W,3] -> conv3x3(3->32) -> conv3x3/2(32->64), one kernel (conv_chain.cu)."""
+    n, h, w, c = img.shape
+    assert c == 3 and img.dtype == torch.uint8
+    d = ChainDesc(n, h, w, 0, ld_y, int(leaky1), int(leaky2))
+    _check(lib().y3_conv_chain_stem_u8(ctypes.byref(d), _ptr(img), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), y_ptr,
+                                       _stream()))
+
+
+def conv_chain_res64(x_ptr, w1, b1, w2, b2, y_ptr, *, n, h, w, ld_x, ld_y, leaky1=True, leaky2=True):
+    """Residual unit x -> conv1x1(64->32) -> conv3x3(32->64) + x, one kernel (conv_chain.cu)."""
+    d = ChainDesc(n, h, w, ld_x, ld_y, int(leaky1), int(leaky2))
+    _check(lib().y3_conv_chain_res64(ctypes.byref(d), x_ptr, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), y_ptr,
+                                     _stream()))
 
 
 def maxpool(x_ptr, y_ptr, n, h, w, c, ld_x, ld_y, ksize, stride):

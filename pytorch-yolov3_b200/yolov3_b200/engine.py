@@ -46,7 +46,8 @@ class Engine:
         self.use_graphs = os.environ.get("Y3_NO_GRAPH", "0") != "1"
         self._graphs = {}
         self.conv_flops = 0  # algorithmic 2*MAC per batch, no padding credit
-        self.conv_ops = []   # (block, launch closure, flops) for per-kernel timing in bench.py
+        self.conv_ops = []   # (block, launch closure, flops) for per-kernel timing in bench.py (uint8 programs)
+        self.conv_ops_unfused_stem = []  # blocks 0-1 as separate launches (float32-input programs) when a stem exists
         # device "meta" builds the plan without touching a GPU (host-logic tests); it cannot run
         self.dry = torch.device(device).type == "meta"
         if self.dry:
@@ -195,12 +196,43 @@ class Engine:
         # channels of the input buffer that hold the image itself (centre tap when im2col'ed)
         self.input_image_channels = (4 * cin0, 5 * cin0) if self.first_im2col else (0, cin0)
 
-        ops = []          # closures, executed in order
-        self.op_names = []
+        ops = []          # (closure, group) executed in order; group None = always,
+        self.op_names = []  # "stem_unfused" / "stem_fused" = alternative forms of blocks 0-1 (see run_backbone)
+        self.op_groups = []
 
-        def emit(name, fn):
+        def emit(name, fn, group=None):
             ops.append(fn)
             self.op_names.append(name)
+            self.op_groups.append(group)
+
+        use_chain = os.environ.get("Y3_NO_CHAIN", "0") != "1"
+
+        def conv_geom(j):
+            bj = blocks[j]
+            return bj["size"], bj["stride"], ((bj["size"] - 1) // 2 if "pad" in bj else 0)
+
+        def res_chain_at(i):
+            """conv1x1(64->32) -> conv3x3/1(32->64) -> shortcut back to the 1x1's input: one kernel."""
+            if not use_chain or i + 2 >= nb or blocks[i + 1]["type"] != "convolutional":
+                return False
+            t = fused_into.get(i + 1)
+            if t is None or blocks[t]["type"] != "shortcut" or consumers.get(i) != [i + 1] or i in fused_into:
+                return False
+            src = inputs_of(i)[0]
+            if src == INPUT or residual_of.get(i + 1) != src or views[src].C != 64 or views[src].f32:
+                return False
+            if conv_geom(i) != (1, 1, 0) or conv_geom(i + 1) != (3, 1, 1):
+                return False
+            if blocks[i]["filters"] != 32 or blocks[i + 1]["filters"] != 64 or is_head(i) or is_head(i + 1):
+                return False
+            return views[src].H % 16 == 0 and views[src].W % 8 == 0
+
+        # blocks 0-1 as conv3x3(3->32) -> conv3x3/2(32->64) straight from uint8 images: one kernel
+        self.stem = None
+        stem_ok = (use_chain and self.first_im2col and cin0 == 3 and nb > 2 and b0["filters"] == 32
+                   and blocks[1]["type"] == "convolutional" and conv_geom(1) == (3, 2, 1)
+                   and blocks[1]["filters"] == 64 and consumers.get(0) == [1] and 0 not in fused_into
+                   and 1 not in fused_into and not is_head(1) and self.H % 32 == 0 and self.W % 32 == 0)
 
         folded = self._folded_weights
 
@@ -210,7 +242,22 @@ class Engine:
             t = b["type"]
             if i in done or i in fused_blocks:
                 continue
-            if t == "convolutional":
+            if t == "convolutional" and res_chain_at(i):
+                xin = views[inputs_of(i)[0]]
+                tgt = fused_into[i + 1]
+                yv = alloc(tgt)
+                views[tgt] = views[i + 1] = yv
+                w1, b1 = folded(i, 64, 32)
+                w2, b2 = folded(i + 1, 32, 64)
+                fn = (lambda xp=xin.ptr, w1=w1, b1=b1, w2=w2, b2=b2, yp=yv.ptr, h=xin.H, w=xin.W, lx=xin.ld, ly=yv.ld,
+                      l1=blocks[i]["activation"] == "leaky", l2=blocks[i + 1]["activation"] == "leaky":
+                      _lib.conv_chain_res64(xp, w1, b1, w2, b2, yp, n=B, h=h, w=w, ld_x=lx, ld_y=ly, leaky1=l1, leaky2=l2))
+                emit(f"chain{i}", fn)
+                flops = 2 * B * xin.H * xin.W * (32 * 64 + 64 * 32 * 9)
+                self.conv_flops += flops
+                self.conv_ops.append((i, fn, flops))
+                done.add(i + 1)
+            elif t == "convolutional":
                 xin = views[inputs_of(i)[0]]
                 k, s = b["size"], b["stride"]
                 pad = (k - 1) // 2 if "pad" in b else 0
@@ -241,12 +288,26 @@ class Engine:
                           res_ptr=res.ptr if res else None, ld_res=res.ld if res else 0, out_f32=head,
                           upsample2x=up)
                 fn = (lambda xp=xin.ptr, w=w, bias=bias, yp=yv.ptr, kw=kw: _lib.conv2d(xp, w, bias, yp, **kw))
-                emit(f"conv{i}", fn)
+                in_stem = stem_ok and i in (0, 1)
+                emit(f"conv{i}", fn, "stem_unfused" if in_stem else None)
                 ho, wo = shape[i][1], shape[i][2]
                 cin_real = cin0 if inputs_of(i)[0] == INPUT else shape[inputs_of(i)[0]][0]
                 flops = 2 * B * ho * wo * cout * cin_real * k * k
                 self.conv_flops += flops
-                self.conv_ops.append((i, fn, flops))
+                if in_stem:
+                    self.conv_ops_unfused_stem.append((i, fn, flops))
+                else:
+                    self.conv_ops.append((i, fn, flops))
+                if in_stem and i == 1:
+                    (w1, b1), (w2, b2) = self._stem_w0, (w, bias)
+                    sfn = (lambda w1=w1, b1=b1, w2=w2, b2=b2, yp=yv.ptr, ly=yv.ld,
+                           l1=blocks[0]["activation"] == "leaky", l2=b["activation"] == "leaky":
+                           _lib.conv_chain_stem_u8(self.in_u8, w1, b1, w2, b2, yp, ld_y=ly, leaky1=l1, leaky2=l2))
+                    emit("stem0", sfn, "stem_fused")
+                    self.stem = sfn
+                    self.conv_ops.insert(0, (0, sfn, sum(f for _, _, f in self.conv_ops_unfused_stem)))
+                elif in_stem:
+                    self._stem_w0 = (w, bias)
                 if head:
                     heads.append((i + 1, yv))
             elif t == "maxpool":
@@ -400,9 +461,14 @@ class Engine:
     # ------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------
-    def run_backbone(self):
-        for op in self.backbone_ops:
-            op()
+    def run_backbone(self, fused_stem=False):
+        """All block launches in order.  Blocks 0-1 exist in two forms when the plan has a stem:
+        separate convolutions over the packed input buffer (float32 input), or the fused
+        uint8-image kernel (`fused_stem`, uint8 programs — no packing launch needed)."""
+        skip = "stem_unfused" if (fused_stem and self.stem is not None) else "stem_fused"
+        for op, group in zip(self.backbone_ops, self.op_groups):
+            if group != skip:
+                op()
 
     def _decode_dense(self):
         for d, logits in self.head_descs:
@@ -434,13 +500,15 @@ class Engine:
                 self._decode_dense()
         elif kind == "det_u8":
             def fn():
-                pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self.run_backbone()
+                if self.stem is None:
+                    pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                self.run_backbone(fused_stem=True)
                 self._detect_tail(key[1], key[2])
         elif kind == "nms_u8":  # inference(): final arrays are emitted by a second launch (Engine.emit)
             def fn():
-                pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self.run_backbone()
+                if self.stem is None:
+                    pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                self.run_backbone(fused_stem=True)
                 self._detect_tail(key[1], key[2], compact=False)
         elif kind == "det_f32":
             def fn():

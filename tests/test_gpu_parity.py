@@ -458,11 +458,21 @@ def teacher_forced_network_check(net, blocks, params, B, size):
     net.forward(x.to(dev()))
     eng = net.engine(B, size, size)
     worst = (0.0, -1)
+    chained = {int(n[5:]) for n in eng.op_names if n.startswith("chain")}
     for i, b in enumerate(blocks):
-        if b["type"] != "convolutional":
+        if b["type"] != "convolutional" or (i - 1) in chained:
             continue
         src = alias_root(blocks, i - 1)
         xin = view_to_nchw(eng.views[src], B)
+        if i in chained:  # conv1x1 -> conv3x3 -> +x in one kernel; the intermediate is bf16 on chip
+            with torch.no_grad():
+                mid = DO.conv_block(xin, b, params[i]).bfloat16().float()
+                ref = DO.conv_block(mid, blocks[i + 1], params[i + 1]) + xin
+            got = view_to_nchw(eng.views[i + 2], B)
+            e = rel_err(got, ref)
+            worst = max(worst, (e, i))
+            assert e <= CONV_TOL, (i, e)
+            continue
         if src < 0:  # network input: stored channel-padded, or im2col'ed (image = centre tap)
             c_lo, c_hi = eng.input_image_channels
             xin = xin[:, c_lo:c_hi]
@@ -552,6 +562,105 @@ def test_yolov3_tiny_416_end_to_end(tmp_path_factory):
     for thr in (0.99, 0.5):
         m, t = match_rate(res, full, thr)
         print(f"yolov3-tiny@416 e2e vs fp32 oracle: {m}/{t} detections matched at IoU>={thr}, same class (reported)")
+
+
+def _rand_conv(g, cout, cin, k):
+    return {"weight": torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5,
+            "bias": torch.randn(cout, generator=g) * 0.2}
+
+
+@pytest.mark.parametrize("n,H,W", [(1, 32, 32), (2, 64, 96), (3, 416, 416)])
+def test_conv_chain_stem_equals_unfused_launches_and_oracle(n, H, W):
+    """uint8 image -> conv0 -> conv1 in one kernel: bit-identical to im2col + two y3_conv2d launches
+    (same bf16 intermediate, same accumulation order) and within the conv bar of the fp32 oracle."""
+    g = torch.Generator().manual_seed(31)
+    u = torch.randint(0, 256, (n, H, W, 3), generator=g, dtype=torch.uint8)
+    p0, p1 = _rand_conv(g, 32, 3, 3), _rand_conv(g, 64, 32, 3)
+    w0 = torch.zeros(32, 32)
+    w0[:, :27] = p0["weight"].permute(0, 2, 3, 1).reshape(32, 27)
+    w0 = w0.to(dev(), torch.bfloat16).contiguous()
+    b0 = p0["bias"].to(dev()).contiguous()
+    w1, b1 = fold(p1, 32, 64)
+    ud = u.to(dev())
+    y = torch.full((n, H // 2, W // 2, 64), 7.0, device=dev(), dtype=torch.bfloat16)
+    _lib.conv_chain_stem_u8(ud, w0, b0, w1, b1, y.data_ptr(), ld_y=64)
+    # unfused launches
+    col = torch.empty(n, H, W, 32, device=dev(), dtype=torch.bfloat16)
+    _lib.im2col3x3_bgr_u8(ud, col, 32)
+    a0 = torch.empty(n, H, W, 32, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(col.data_ptr(), w0, b0, a0.data_ptr(), n=n, h=H, w_in=W, cin=32, cout=32, ksize=1, stride=1, pad=0,
+                ld_x=32, ld_y=32, leaky=True)
+    a1 = torch.empty(n, H // 2, W // 2, 64, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(a0.data_ptr(), w1, b1, a1.data_ptr(), n=n, h=H, w_in=W, cin=32, cout=64, ksize=3, stride=2, pad=1,
+                ld_x=32, ld_y=64, leaky=True)
+    torch.cuda.synchronize()
+    assert torch.equal(y, a1), float((y.float() - a1.float()).abs().max())
+    if H <= 96:  # fp32 oracle on the reference's own preprocessing
+        xf = torch.from_numpy(PO.preprocess(list(u.numpy())))
+        mid = F.leaky_relu(F.conv2d(xf.bfloat16().float(), p0["weight"].bfloat16().float(), p0["bias"], padding=1), 0.1)
+        ref = F.leaky_relu(F.conv2d(mid.bfloat16().float(), p1["weight"].bfloat16().float(), p1["bias"], stride=2,
+                                    padding=1), 0.1)
+        assert rel_err(y.float().cpu().permute(0, 3, 1, 2), ref) <= CONV_TOL
+
+
+@pytest.mark.parametrize("n,H,W,ld", [(1, 16, 8, 64), (2, 48, 40, 64), (5, 208, 208, 64), (2, 32, 24, 96)])
+def test_conv_chain_res64_equals_unfused_launches_and_oracle(n, H, W, ld):
+    """x -> conv1x1 -> conv3x3 -> +x in one kernel vs the two y3_conv2d launches (second with the
+    fused shortcut) and vs the fp32 oracle; ld > 64 = x and y are channel slices of wider buffers."""
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(n, 64, H, W, generator=g)
+    p0, p1 = _rand_conv(g, 32, 64, 1), _rand_conv(g, 64, 32, 3)
+    w0, b0 = fold(p0, 64, 32)
+    w1, b1 = fold(p1, 32, 64)
+    xbuf = torch.zeros(n, H, W, ld, device=dev(), dtype=torch.bfloat16)
+    xbuf[..., :64] = nhwc_bf16(x)
+    ybuf = torch.full((n, H, W, ld), 3.0, device=dev(), dtype=torch.bfloat16)
+    _lib.conv_chain_res64(xbuf.data_ptr(), w0, b0, w1, b1, ybuf.data_ptr(), n=n, h=H, w=W, ld_x=ld, ld_y=ld)
+    mid = torch.empty(n, H, W, 32, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(xbuf.data_ptr(), w0, b0, mid.data_ptr(), n=n, h=H, w_in=W, cin=64, cout=32, ksize=1, stride=1, pad=0,
+                ld_x=ld, ld_y=32, leaky=True)
+    y2 = torch.empty(n, H, W, 64, device=dev(), dtype=torch.bfloat16)
+    _lib.conv2d(mid.data_ptr(), w1, b1, y2.data_ptr(), n=n, h=H, w_in=W, cin=32, cout=64, ksize=3, stride=1, pad=1,
+                ld_x=32, ld_y=64, leaky=True, res_ptr=xbuf.data_ptr(), ld_res=ld)
+    torch.cuda.synchronize()
+    assert torch.equal(ybuf[..., :64], y2), float((ybuf[..., :64].float() - y2.float()).abs().max())
+    if ld > 64:
+        assert float((ybuf[..., 64:].float() - 3.0).abs().max()) == 0  # neighbouring channels untouched
+    if H <= 48:
+        xr = xbuf[..., :64].float().cpu().permute(0, 3, 1, 2)
+        m = F.leaky_relu(F.conv2d(xr, p0["weight"].bfloat16().float(), p0["bias"]), 0.1).bfloat16().float()
+        ref = F.leaky_relu(F.conv2d(m, p1["weight"].bfloat16().float(), p1["bias"], padding=1), 0.1) + xr
+        assert rel_err(y2.float().cpu().permute(0, 3, 1, 2), ref) <= CONV_TOL
+
+
+def test_conv_chain_rejects_bad_arguments():
+    z = torch.zeros(1, 32, 32, 64, device=dev(), dtype=torch.bfloat16)
+    w0, w1 = torch.zeros(32, 64, device=dev(), dtype=torch.bfloat16), torch.zeros(64, 288, device=dev(), dtype=torch.bfloat16)
+    b0, b1 = torch.zeros(32, device=dev()), torch.zeros(64, device=dev())
+    with pytest.raises(RuntimeError, match="tile"):  # 20 rows do not tile by 16
+        _lib.conv_chain_res64(z.data_ptr(), w0, b0, w1, b1, z.data_ptr() + 4096, n=1, h=20, w=32, ld_x=64, ld_y=64)
+    with pytest.raises(RuntimeError, match="in-place"):
+        _lib.conv_chain_res64(z.data_ptr(), w0, b0, w1, b1, z.data_ptr(), n=1, h=32, w=32, ld_x=64, ld_y=64)
+    u = torch.zeros(1, 40, 40, 3, device=dev(), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="tile"):
+        _lib.conv_chain_stem_u8(u, w0, b0, w1, b1, z.data_ptr(), ld_y=64)
+
+
+def test_uint8_stem_program_equals_float_program(yolov3_full):
+    """inference()'s program (fused uint8 stem) and Darknet.forward's (packed float input, blocks 0-1
+    as separate launches) must produce identical head logits for the same pixels."""
+    net, *_ = yolov3_full
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
+    eng = net.engine(2, 416, 416)
+    assert eng.stem is not None and any(n.startswith("chain") for n in eng.op_names)
+    net.forward(torch.from_numpy(PO.preprocess(list(imgs))).to(dev()))
+    torch.cuda.synchronize()
+    want = [logits.clone() for _, logits in eng.head_descs]
+    yolov3_b200.inference(net, list(imgs), device="cuda:0", prob_thresh=0.05, resize=False)
+    torch.cuda.synchronize()
+    for (_, logits), w in zip(eng.head_descs, want):
+        assert torch.equal(logits, w)
 
 
 def test_first_layer_im2col_packing_matches_unfold():

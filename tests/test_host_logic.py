@@ -81,7 +81,15 @@ def test_execution_plan_fuses_everything(name, size, convs, shortcuts, upsamples
     net = yolov3_b200.Darknet(f"{MODELS}/{name}.cfg", device="cuda")
     eng = Engine(net, 2, size, size, torch.device("meta"))
     kinds = [re.sub(r"[\d_]+$", "", n) for n in eng.op_names]
-    assert kinds.count("conv") == convs
+    # every conv block is covered exactly once per program: a residual chain stands for two convs,
+    # the uint8 stem is the alternative form of blocks 0-1 (which stay as convs for float32 input)
+    assert kinds.count("conv") + 2 * kinds.count("chain") == convs
+    if name != "yolov3-tiny":
+        assert kinds.count("chain") == 1 and kinds.count("stem") == 1 and eng.stem is not None
+        assert eng.op_groups.count("stem_unfused") == 2 and eng.op_groups.count("stem_fused") == 1
+        assert len(eng.conv_ops) == convs - 2  # stem + chain each time two blocks as one launch
+    else:
+        assert eng.stem is None and "chain" not in kinds
     assert "add" not in kinds and "upsample" not in kinds and "copy" not in kinds  # all fused / zero-copy
     assert eng.num_fused["shortcut"] == shortcuts and eng.num_fused["upsample"] == upsamples
     assert eng.M == M and eng.num_classes == 80
@@ -178,7 +186,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.y3_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.y3_abi_version() == _lib.ABI_VERSION == 3
     lib.y3_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.y3_last_error(), bytes)
 
