@@ -18,7 +18,7 @@
 //            8-pixel groups through SBO; stride 2 by viewing pixel pairs as 128-byte rows)
 //   epi 2    +bias, leaky, (+x from the patch already in smem) -> swizzled slab -> 4-D TMA store
 // Weights of both layers stay resident in smem for the whole kernel.  Teams are not pipelined
-// internally; two teams per SM overlap each other's phases.
+// internally; three teams per SM overlap each other's phases.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -34,7 +34,7 @@ constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
 template <int MODE>
 struct ChainCfg {
   static constexpr bool STEM = MODE == CHAIN_STEM;
-  static constexpr int TEAMS = 2;
+  static constexpr int TEAMS = 3;
   static constexpr int TEAM_THREADS = 128;
   static constexpr int THREADS = TEAMS * TEAM_THREADS;
   static constexpr int TW = 8, TH = 16;             // stage-2 output tile (M = 128 rows = 16 groups of 8)
@@ -49,25 +49,29 @@ struct ChainCfg {
   static constexpr int W1_BYTES = CM * A1_SPAN;     // 2048 | 4096
   static constexpr int W2_TAP_BYTES = C2 * CM * 2;  // 4096
   static constexpr int W2_BYTES = 9 * W2_TAP_BYTES;
-  // team-private regions (all 1024B-aligned)
-  static constexpr int A1_BYTES = STEM ? MT1 * 128 * A1_SPAN : round_up_c(NP * A1_SPAN, 1024);  // 40960 | 23552
+  static constexpr int BIAS_BYTES = (CM + C2) * 4;  // both bias vectors, read as broadcast LDS.128
+  // Team-private regions.  Swizzles are functions of the absolute smem address, so operands only need
+  // 128-byte alignment: STEM's intermediate patch overlays the (dead) im2col rows; RES's two x-patch
+  // buffers are packed back to back and the output slab overlays the (dead) intermediate.
+  static constexpr int A1_BYTES = STEM ? MT1 * 128 * A1_SPAN : NP * A1_SPAN;  // 40960 | 23040
   static constexpr int A1_BUFS = STEM ? 1 : 2;      // RES: x patch of the next tile is prefetched
-  static constexpr int MID_BYTES = round_up_c(NP * CM * 2, 1024);  // 38912 | 12288
-  static constexpr int STG_BYTES = 128 * C2 * 2;    // 16384; STEM: aliases the (dead) intermediate patch
+  static constexpr int STG_BYTES = 128 * C2 * 2;    // 16384
   static constexpr int IMG_ROWS = PH + 2, IMG_PITCH = 60;           // STEM image patch: 35 rows x 20 px x 3
   static constexpr int IMG_BYTES = STEM ? round_up_c(IMG_ROWS * IMG_PITCH * 2, 1024) : 0;
-  static constexpr int OFF_MID = A1_BUFS * A1_BYTES;
-  static constexpr int OFF_STG = STEM ? OFF_MID : OFF_MID + MID_BYTES;
-  static constexpr int OFF_IMG = OFF_MID + MID_BYTES + (STEM ? 0 : STG_BYTES);
-  static constexpr int TEAM_BYTES = OFF_IMG + IMG_BYTES;
-  static constexpr int D2_COL = MT1 * CM;           // TMEM column of the stage-2 accumulator
-  static constexpr int TMEM_COLS_TEAM = STEM ? 256 : 128;
-  static constexpr int TMEM_COLS = TEAMS * TMEM_COLS_TEAM;
-  static constexpr int SMEM_BYTES = 1024 + W1_BYTES + W2_BYTES + TEAMS * TEAM_BYTES + 256;
+  static constexpr int OFF_MID = STEM ? 0 : A1_BUFS * A1_BYTES;     // 0 | 46080
+  static constexpr int OFF_STG = STEM ? A1_BYTES : OFF_MID;         // 40960 | 46080
+  static constexpr int OFF_IMG = OFF_STG + STG_BYTES;
+  static constexpr int TEAM_BYTES = OFF_IMG + IMG_BYTES;            // 62464 | 62464
+  static_assert(TEAM_BYTES % 1024 == 0 && OFF_STG % 1024 == 0 && OFF_MID % 1024 == 0, "region alignment");
+  static_assert(NP * CM * 2 <= (STEM ? A1_BYTES : STG_BYTES), "intermediate patch must fit its overlay");
+  // the stage-2 accumulator overlays the stage-1 accumulators (drained by epilogue 1 before stage 2 starts)
+  static constexpr int TMEM_COLS_TEAM = MT1 * CM;   // 160 | 64
+  static constexpr int TMEM_COLS = TEAMS * TMEM_COLS_TEAM <= 256 ? 256 : 512;
+  static_assert(TEAMS * TMEM_COLS_TEAM <= 512 && C2 <= TMEM_COLS_TEAM, "TMEM budget");
+  static constexpr int SMEM_BYTES = 1024 + W1_BYTES + W2_BYTES + TEAMS * TEAM_BYTES + BIAS_BYTES + 256;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert(D2_COL + C2 <= TMEM_COLS_TEAM, "TMEM budget");
-  // stage-1 over-read of the last M tile must stay inside the team region
-  static_assert(STEM || (A1_BYTES + MT1 * 128 * A1_SPAN <= TEAM_BYTES), "RES stage-1 over-read");
+  // stage-1 over-read of the last M tile (rows NP..MT1*128) must stay inside the team region
+  static_assert(STEM || ((A1_BUFS - 1) * A1_BYTES + MT1 * 128 * A1_SPAN <= TEAM_BYTES), "RES stage-1 over-read");
   static constexpr int IMG_U16 = IMG_ROWS * (IMG_PITCH / 2);  // 1050 two-byte loads per image patch
   static constexpr int IMG_PRE = (IMG_U16 + TEAM_THREADS - 1) / TEAM_THREADS;  // 9 per thread
 };
@@ -113,7 +117,8 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t w1_s = smem_base;
   const uint32_t w2_s = w1_s + Cfg::W1_BYTES;
   const uint32_t teams_s = w2_s + Cfg::W2_BYTES;
-  const uint32_t bar_base = teams_s + Cfg::TEAMS * Cfg::TEAM_BYTES;
+  const uint32_t bias_s = teams_s + Cfg::TEAMS * Cfg::TEAM_BYTES;  // bias1[CM] then bias2[C2], fp32
+  const uint32_t bar_base = bias_s + Cfg::BIAS_BYTES;
   const uint32_t wbar = bar_base;                            // weights landed
   const uint32_t tmem_slot = bar_base + 8;
   const int team = threadIdx.x >> 7;
@@ -145,6 +150,10 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     ptx::tmem_alloc<1>(tmem_slot, Cfg::TMEM_COLS);
     ptx::tmem_relinquish<1>();
   }
+  if (threadIdx.x < Cfg::CM + Cfg::C2) {  // biases are constants: no dependency on the previous kernel
+    float* const bias_gen = reinterpret_cast<float*>(smem_gen + (bias_s - smem_base));
+    bias_gen[threadIdx.x] = threadIdx.x < Cfg::CM ? __ldg(p.bias1 + threadIdx.x) : __ldg(p.bias2 + threadIdx.x - Cfg::CM);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -161,6 +170,8 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int team_step = gridDim.x * Cfg::TEAMS;
   const uint32_t bar_id = 1 + team;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const float slope1 = p.leaky1 ? 0.1f : 1.0f;  // leaky(v) = max(v, 0.1 v); identity = max(v, v)
+  const float slope2 = p.leaky2 ? 0.1f : 1.0f;
   auto tile_origin = [&](int tile, int& b, int& y0, int& x0) {
     b = tile / tiles_per_img;
     const int rem = tile - b * tiles_per_img;
@@ -169,24 +180,44 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     x0 = (rem - ty * p.tiles_x) * Cfg::TW;
   };
 
-  // ---- STEM: register prefetch of the next tile's uint8 patch (two bytes per load) ----
+  // ---- STEM: register prefetch of the next tile's uint8 patch (two bytes per load).  Element e of the
+  // patch (row r = e/30, byte pair c = e%30) belongs to this thread for e = i*128 + tid; (r, c) and the
+  // bf16 destinations of its two bytes do not depend on the tile and are computed once.
   uint32_t pre[STEM ? Cfg::IMG_PRE : 1];
+  uint32_t pre_rc[STEM ? Cfg::IMG_PRE : 1];   // r | c << 8 | valid << 16
+  uint32_t pre_dst[STEM ? Cfg::IMG_PRE : 1];  // patch index of byte 0 | of byte 1 << 16
+  if constexpr (STEM) {
+#pragma unroll
+    for (int i = 0; i < Cfg::IMG_PRE; ++i) {
+      const int e = i * Cfg::TEAM_THREADS + tid;
+      const int r = e / (Cfg::IMG_PITCH / 2);
+      const int c = e - r * (Cfg::IMG_PITCH / 2);
+      pre_rc[i] = uint32_t(r) | (uint32_t(c) << 8) | (e < Cfg::IMG_U16 ? 1u << 16 : 0u);
+      uint32_t d[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * c + h;  // byte column: pixel j/3, BGR byte j%3 -> RGB channel 2 - j%3
+        const int px = j / 3;
+        d[h] = uint32_t(r * Cfg::IMG_PITCH + px * 3 + (2 - (j - px * 3)));
+      }
+      pre_dst[i] = d[0] | (d[1] << 16);
+      pre[i] = 0;
+    }
+  }
   auto img_prefetch = [&](int tile) {
     if constexpr (STEM) {
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
       const int byte0 = 6 * x0 - 6;  // first byte of the patch row inside the image row (even)
       const int row_bytes = 3 * p.Wm;
+      const uint8_t* const base = p.img + (long long)b * p.Hm * row_bytes;
 #pragma unroll
       for (int i = 0; i < Cfg::IMG_PRE; ++i) {
-        const int e = i * Cfg::TEAM_THREADS + tid;
-        const int r = e / (Cfg::IMG_PITCH / 2);
-        const int c = e - r * (Cfg::IMG_PITCH / 2);
-        const int iy = 2 * y0 - 2 + r;
-        const int byte = byte0 + 2 * c;
-        const bool ok = e < Cfg::IMG_U16 && iy >= 0 && iy < p.Hm && byte >= 0 && byte < row_bytes;
+        const int iy = 2 * y0 - 2 + int(pre_rc[i] & 0xffu);
+        const int byte = byte0 + 2 * int((pre_rc[i] >> 8) & 0xffu);
+        const bool ok = (pre_rc[i] >> 16) != 0 && iy >= 0 && iy < p.Hm && byte >= 0 && byte < row_bytes;
         uint32_t v = 0;
-        if (ok) v = __ldg(reinterpret_cast<const unsigned short*>(p.img + ((long long)b * p.Hm + iy) * row_bytes + byte));
+        if (ok) v = __ldg(reinterpret_cast<const unsigned short*>(base + (long long)iy * row_bytes + byte));
         pre[i] = v;
       }
     }
@@ -214,22 +245,16 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t a1_s = team_s + cur * Cfg::A1_BYTES;
 
     if constexpr (STEM) {
-      // (1) image bytes -> bf16 RGB/255 patch [35][20 px][3]  (inference.py:332-333)
+      // (1) image bytes -> bf16 RGB/255 patch [35][20 px][3]  (inference.py:332-333).  v * fl(1/255)
+      // rounds to the same bf16 as the reference's fp32 v / 255 for all 256 byte values.
       __nv_bfloat16* const patch = reinterpret_cast<__nv_bfloat16*>(smem_gen + (team_s + Cfg::OFF_IMG - smem_base));
 #pragma unroll
       for (int i = 0; i < Cfg::IMG_PRE; ++i) {
-        const int e = i * Cfg::TEAM_THREADS + tid;
-        if (e < Cfg::IMG_U16) {
-          const int r = e / (Cfg::IMG_PITCH / 2);
-          const int c = e - r * (Cfg::IMG_PITCH / 2);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = 2 * c + h;       // byte column: pixel j/3, BGR byte j%3
-            const int px = j / 3;
-            const int bch = j - px * 3;
-            const float v = __fmul_rn((float)((pre[i] >> (8 * h)) & 0xffu), 0.003921568859368563f);
-            patch[r * Cfg::IMG_PITCH + px * 3 + (2 - bch)] = __float2bfloat16_rn(v);
-          }
+        if (pre_rc[i] >> 16) {
+          const float v0 = __fmul_rn((float)(pre[i] & 0xffu), 0.003921568859368563f);
+          const float v1 = __fmul_rn((float)((pre[i] >> 8) & 0xffu), 0.003921568859368563f);
+          patch[pre_dst[i] & 0xffffu] = __float2bfloat16_rn(v0);
+          patch[pre_dst[i] >> 16] = __float2bfloat16_rn(v1);
         }
       }
       ptx::named_bar_sync(bar_id, Cfg::TEAM_THREADS);
@@ -265,7 +290,8 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       ptx::mbar_wait(xbar0 + 8u * cur, (it >> 1) & 1);
     }
-    // the previous tile's TMA store must have finished reading the slab (STEM: = the patch below)
+    // the previous tile's TMA store must have finished reading the slab before anyone rewrites it
+    // (RES: the slab is also the intermediate patch written by epilogue 1)
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     ptx::tc_fence_before();
     ptx::named_bar_sync(bar_id, Cfg::TEAM_THREADS);
@@ -292,9 +318,9 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t tlane = uint32_t(warp * 32) << 16;
 #pragma unroll 1
     for (int t = 0; t < Cfg::MT1; ++t) {
-      uint32_t v0[16], v1[16];
-      ptx::tmem_ld_x16(tmem_team + tlane + t * Cfg::CM, v0);
-      ptx::tmem_ld_x16(tmem_team + tlane + t * Cfg::CM + 16, v1);
+      uint32_t v[32];
+      ptx::tmem_ld_x16(tmem_team + tlane + t * Cfg::CM, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      ptx::tmem_ld_x16(tmem_team + tlane + t * Cfg::CM + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
       ptx::tmem_ld_wait();
       const int pi = t * 128 + warp * 32 + lane;
       if (pi < Cfg::NP) {
@@ -303,26 +329,23 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int my = y0 * Cfg::S2 - 1 + mr;
         const int mx = x0 * Cfg::S2 - 1 + mc;
         const bool inside = my >= 0 && my < p.Hm && mx >= 0 && mx < p.Wm;
-        uint32_t w[16];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float2 bq = __ldg(reinterpret_cast<const float2*>(p.bias1) + q);
-          float a = __uint_as_float(v0[2 * q]) + bq.x, c = __uint_as_float(v0[2 * q + 1]) + bq.y;
-          if (p.leaky1) { a = a > 0.f ? a : 0.1f * a; c = c > 0.f ? c : 0.1f * c; }
-          w[q] = inside ? pack_bf16x2(a, c) : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float2 bq = __ldg(reinterpret_cast<const float2*>(p.bias1) + 8 + q);
-          float a = __uint_as_float(v1[2 * q]) + bq.x, c = __uint_as_float(v1[2 * q + 1]) + bq.y;
-          if (p.leaky1) { a = a > 0.f ? a : 0.1f * a; c = c > 0.f ? c : 0.1f * c; }
-          w[8 + q] = inside ? pack_bf16x2(a, c) : 0u;
-        }
         const uint32_t row = mid_s + pi * (Cfg::CM * 2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          const uint4 ba = lds128(bias_s + c * 32), bb = lds128(bias_s + c * 32 + 16);
+          const float bq[8] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w),
+                               __uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float a = __uint_as_float(v[8 * c + 2 * q]) + bq[2 * q];
+            float d = __uint_as_float(v[8 * c + 2 * q + 1]) + bq[2 * q + 1];
+            a = fmaxf(a, slope1 * a);
+            d = fmaxf(d, slope1 * d);
+            w[q] = inside ? pack_bf16x2(a, d) : 0u;
+          }
           const uint32_t a = STEM ? swz128(row + c * 16) : swz64(row + c * 16);
-          sts128(a, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+          sts128(a, w[0], w[1], w[2], w[3]);
         }
       }
     }
@@ -342,7 +365,7 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const uint64_t db = chain_desc(w2_s + tap * Cfg::W2_TAP_BYTES, 8 * Cfg::CM * 2, 4);
 #pragma unroll
         for (int k = 0; k < Cfg::CM / 16; ++k)
-          ptx::umma_bf16_ss<1>(tmem_team + Cfg::D2_COL, da + 2u * k, db + 2u * k, chain_idesc(Cfg::C2), (tap | k) != 0);
+          ptx::umma_bf16_ss<1>(tmem_team, da + 2u * k, db + 2u * k, chain_idesc(Cfg::C2), (tap | k) != 0);
       }
       ptx::umma_commit<1>(mma_bar);
     }
@@ -358,21 +381,19 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[16];
-        ptx::tmem_ld_x16(tmem_team + tlane + Cfg::D2_COL + cc * 16, v);
+        ptx::tmem_ld_x16(tmem_team + tlane + cc * 16, v);
         ptx::tmem_ld_wait();
         float f[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias2) + cc * 4 + q);
-          f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bq.x;
-          f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bq.y;
-          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bq.z;
-          f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bq.w;
+          const uint4 bq = lds128(bias_s + Cfg::CM * 4 + cc * 64 + q * 16);
+          f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + __uint_as_float(bq.x);
+          f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + __uint_as_float(bq.y);
+          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(bq.z);
+          f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(bq.w);
         }
-        if (p.leaky2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-        }
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope2 * f[j]);
         if constexpr (!STEM) {
           const uint4 r0 = lds128(swz128(rrow + (2 * cc) * 16));
           const uint4 r1 = lds128(swz128(rrow + (2 * cc + 1) * 16));
