@@ -22,6 +22,8 @@ static constexpr int MAX_CLASSES = 1024;
 struct Box4 { int x1, y1, x2, y2; };
 
 __device__ __forceinline__ bool iou_gt(const Box4& a, const Box4& b, double thr) {
+  // disjoint boxes (iw <= 0 or ih <= 0): the intersection is exactly 0, no 64-bit work needed
+  if (min(a.x2, b.x2) < max(a.x1, b.x1) || min(a.y2, b.y2) < max(a.y1, b.y1)) return 0.0 > thr;
   const long long area_a = ((long long)a.x2 - a.x1 + 1) * ((long long)a.y2 - a.y1 + 1);
   const long long area_b = ((long long)b.x2 - b.x1 + 1) * ((long long)b.y2 - b.y1 + 1);
   long long iw = (long long)min(a.x2, b.x2) - (long long)max(a.x1, b.x1) + 1;
@@ -114,7 +116,7 @@ static constexpr int BITMASK_WORDS = BITMASK_MAX / 32;
 __global__ void __launch_bounds__(1024)
 nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
                    int cap, int C, double thr, y3_cand* __restrict__ sorted,
-                   uint8_t* __restrict__ keep, int* __restrict__ class_kept) {
+                   uint8_t* __restrict__ keep, int* __restrict__ class_kept, int min_n) {
   pdl_enter();
   __shared__ int4 sbox[BITMASK_MAX];
   __shared__ float skey_p[BITMASK_MAX];
@@ -129,6 +131,7 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
     if (class_kept && threadIdx.x == 0) class_kept[(long long)img * C + seg] = 0;
     return;
   }
+  if (n < min_n) return;  // done by nms_bitmask_kernel
   const y3_cand* src = bucketed + (long long)img * cap + off;
   y3_cand* out = sorted + (long long)img * cap + off;
   uint8_t* keep_out = keep + (long long)img * cap + off;
@@ -300,6 +303,163 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
   }
 }
 
+// Segments of up to FAST_SEG_MAX boxes — every per-class segment of a real detector output — in three
+// size classes (<= 128, <= 256, <= 512 boxes), one CTA of MAXN threads per (image, class):
+//   1. rank sort by (prob desc, box asc) through shared memory; the sorted boxes are kept there as
+//      fp32 (x1, y1, x2+1, y2+1) + area;
+//   2. warp w owns the 32 boxes of column block w in registers and walks the pivots i < 32(w+1): the
+//      pivot is a shared-memory broadcast, 32 lanes test at once, __ballot_sync makes the word
+//      "pivot i suppresses boxes 32w..32w+31";
+//   3. one warp resolves the greedy order from the bit matrix, 32 boxes per step.
+// The IoU decision is made in fp32 with a 2^-18 guard band around the threshold (coordinates below
+// 2^22 are exact in fp32; the accumulated rounding of inter / union stays under 2^-20); only pairs
+// inside the band, or involving a box with huge or degenerate coordinates (area stored as NaN, which
+// fails both band comparisons), evaluate the reference's int64 / float64 expression (iou_gt) — the
+// kept set stays bit-exact.  Larger segments are left to nms_segment_kernel.
+static constexpr int FAST_SEG_MAX = 512;
+
+__device__ __forceinline__ float fast_area(int x1, int y1, int x2, int y2) {
+  const bool small = x1 > -4194304 && x1 <= x2 && x2 < 4194304 && y1 > -4194304 && y1 <= y2 && y2 < 4194304;
+  return small ? __fmul_rn((float)(x2 - x1 + 1), (float)(y2 - y1 + 1)) : __int_as_float(0x7fc00000);
+}
+
+template <int MAXN>
+__global__ void __launch_bounds__(MAXN)
+nms_bitmask_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off, int cap, int C,
+                   double thr, y3_cand* __restrict__ sorted, uint8_t* __restrict__ keep,
+                   int* __restrict__ class_kept, int min_n) {
+  pdl_enter();
+  constexpr int WORDS = MAXN / 32;
+  __shared__ float4 sboxf[MAXN];
+  __shared__ float sarea[MAXN];
+  __shared__ uint2 skey[MAXN];
+  __shared__ uint32_t smask[WORDS][MAXN + 1];  // [w][i]; +1: the scan reads one column across w
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x;
+  const int img = blockIdx.y;
+  const int seg = blockIdx.x;
+  const int off = seg_off[(long long)img * (C + 1) + seg];
+  const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
+  if (n <= 0) {
+    if (class_kept && t == 0) class_kept[(long long)img * C + seg] = 0;
+    return;
+  }
+  if (n <= min_n || n > MAXN) return;  // another size class (or nms_segment_kernel) owns this segment
+  const y3_cand* src = bucketed + (long long)img * cap + off;
+  y3_cand* out = sorted + (long long)img * cap + off;
+  uint8_t* keep_out = keep + (long long)img * cap + off;
+
+  // ---- 1. rank sort -------------------------------------------------------------------------------
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+  if (t < n) {
+    lo = reinterpret_cast<const uint4*>(src + t)[0];
+    hi = reinterpret_cast<const uint4*>(src + t)[1];
+    skey[t] = make_uint2(hi.x, hi.z);
+  }
+  __syncthreads();
+  if (t < n) {
+    const float p = __uint_as_float(hi.x);
+    const int b = (int)hi.z;
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const uint2 kj = skey[j];
+      rank += before(__uint_as_float(kj.x), (int)kj.y, p, b) ? 1 : 0;
+    }
+    reinterpret_cast<uint4*>(out + rank)[0] = lo;
+    reinterpret_cast<uint4*>(out + rank)[1] = hi;
+    const int x1 = (int)lo.x, y1 = (int)lo.y, x2 = (int)lo.z, y2 = (int)lo.w;
+    sboxf[rank] = make_float4((float)x1, (float)y1, (float)x2 + 1.0f, (float)y2 + 1.0f);
+    sarea[rank] = fast_area(x1, y1, x2, y2);
+  }
+  __syncthreads();
+
+  // ---- 2. bit matrix ------------------------------------------------------------------------------
+  // Work items (w, c), c <= w: the 32 boxes of column block w against the 32 pivots of chunk c, dealt
+  // round-robin to ALL warps of the CTA (a warp-per-column split would leave the first warps idle:
+  // column w meets 32 (w + 1) pivots).  iou > thr  <=>  inter > thr / (1 + thr) * (area_i + area_j).
+  const int words = (n + 31) >> 5;
+  {
+    const double cd = thr / (1.0 + thr);
+    const bool band_ok = thr > 1e-6 && thr < 1e6;  // the guard band assumes a positive finite threshold
+    const float c_hi = band_ok ? (float)cd * (1.0f + 3.814697265625e-06f) : __int_as_float(0x7fc00000);  // 1 + 2^-18
+    const float c_lo = band_ok ? (float)cd * (1.0f - 3.814697265625e-06f) : __int_as_float(0x7fc00000);
+    const int items = words * (words + 1) / 2;
+    for (int item = warp; item < items; item += MAXN / 32) {
+      int w = 0, c = item;
+      while (c > w) { c -= w + 1; ++w; }
+      const int j = 32 * w + lane;
+      const bool jv = j < n;
+      const float4 mb = jv ? sboxf[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ma = jv ? sarea[j] : 1.0f;
+      const int i0 = 32 * c;
+      const int rn = min(32, n - i0);
+      const int jrel = jv ? j - i0 : 0;  // pivot r precedes my box iff r < jrel
+      uint32_t myword = 0;               // lane r keeps the word of pivot i0 + r
+#pragma unroll 4
+      for (int r = 0; r < rn; ++r) {
+        const float4 pv = sboxf[i0 + r];
+        const float s2 = sarea[i0 + r] + ma;
+        const float iw = fminf(pv.z, mb.z) - fmaxf(pv.x, mb.x);
+        const float ih = fminf(pv.w, mb.w) - fmaxf(pv.y, mb.y);
+        const float fi = fmaxf(iw, 0.f) * fmaxf(ih, 0.f);
+        const bool live = r < jrel;
+        bool sup = live && fi > c_hi * s2;
+        // inside the guard band, NaN area, or odd threshold: the reference's exact expression
+        const bool band = live && !sup && !(fi <= c_lo * s2);
+        if (__any_sync(0xffffffffu, band)) {
+          if (band) {
+            const int4 a = reinterpret_cast<const int4*>(out + i0 + r)[0];
+            const int4 b = reinterpret_cast<const int4*>(out + j)[0];
+            sup = iou_gt(Box4{a.x, a.y, a.z, a.w}, Box4{b.x, b.y, b.z, b.w}, thr);
+          }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, sup);
+        if (lane == r) myword = word;
+      }
+      if (lane < rn) smask[w][i0 + lane] = myword;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. greedy scan, 32 boxes per step ------------------------------------------------------------
+  if (warp == 0) {
+    uint32_t removed = 0;  // lane w: bits [32w, 32w+32) of the removed set
+    for (int c = 0; c < words; ++c) {
+      const int i0 = 32 * c;
+      const int cnt = min(32, n - i0);
+      // diagonal block: lane r holds which boxes of this chunk box i0+r suppresses
+      const uint32_t diag = (lane < cnt) ? smask[c][i0 + lane] : 0u;
+      uint32_t rem = __shfl_sync(0xffffffffu, removed, c);
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t dt = __shfl_sync(0xffffffffu, diag, r);  // independent of the chain on `rem`
+        if (!((rem >> r) & 1u)) rem |= dt;
+      }
+      if (lane == c) removed = rem;
+      uint32_t kept = ~rem & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));  // warp-uniform
+      if (lane > c && lane < words) {
+        while (kept) {
+          const int r = __ffs(kept) - 1;
+          kept &= kept - 1;
+          removed |= smask[lane][i0 + r];
+        }
+      }
+    }
+    int nkept = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int i = 32 * lane + b;
+      if (i < n) {
+        const int k = ((removed >> b) & 1u) ? 0 : 1;
+        keep_out[i] = (uint8_t)k;
+        nkept += k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, o);
+    if (class_kept && lane == 0) class_kept[(long long)img * C + seg] = nkept;
+  }
+}
+
 // a17: the three arrays `inference` returns per image (yolov3/inference.py:360-366), written
 // straight in their final dtypes and final order: one warp per (image, class) segment compacts
 // the segment's kept records (already prob-descending) to dst_off[image, class], the position the
@@ -436,9 +596,20 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
                            class_first_box, class_start));
   Y3_LAUNCH_OK("nms_bucket_kernel");
 
+  // segments of <= FAST_SEG_MAX boxes: three size classes of the fp32 bit-matrix kernel; the rest (if any):
+  // nms_segment_kernel.  Each launch covers every segment and returns at once for foreign sizes.
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<128>, dim3(C, n), dim3(128), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           sorted, keep, class_kept, 0));
+  Y3_LAUNCH_OK("nms_bitmask_kernel<128>");
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<256>, dim3(C, n), dim3(256), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           sorted, keep, class_kept, 128));
+  Y3_LAUNCH_OK("nms_bitmask_kernel<256>");
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<512>, dim3(C, n), dim3(512), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           sorted, keep, class_kept, 256));
+  Y3_LAUNCH_OK("nms_bitmask_kernel<512>");
   const int threads = per_class ? 256 : 1024;  // one huge segment per image: more threads per CTA
   Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(dim3(C, n)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh, sorted, keep,
-                           class_kept));
+                           class_kept, FAST_SEG_MAX + 1));
   Y3_LAUNCH_OK("nms_segment_kernel");
   return Y3_OK;
 }
