@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 3
+#define Y3_ABI_VERSION 4
 
 enum {
   Y3_OK = 0,
@@ -214,6 +214,19 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits,
                          float prob_thresh, const int32_t* orig_hw,
                          y3_cand* cands, int32_t* counts, int32_t cap,
                          void* stream);
+
+/*
+ * YOLO head convolution with the decode fused into its epilogue: the 1x1 convolution feeding a
+ * [yolo] block (yolov3/darknet.py:244-261) followed by y3_yolo_decode_cands' arithmetic, applied to
+ * the fp32 accumulator (+ bias) of each pixel while it is still in tensor memory — the logits never
+ * go to HBM.  Requires 3 anchors x 80 classes (255 channels stored as 256; every shipped cfg);
+ * otherwise use y3_conv2d (out_f32) + y3_yolo_decode_cands.  The softmax denominator is summed in
+ * ascending class order, so a probability may differ from y3_yolo_decode_cands' in the last ulp.
+ */
+int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w,
+                        const float* bias, const y3_head_desc* head,
+                        float prob_thresh, const int32_t* orig_hw, y3_cand* cands,
+                        int32_t* counts, int32_t cap, void* stream);
 
 /* ---- a15/a16: non-max suppression ------------------------------------------ */
 /*

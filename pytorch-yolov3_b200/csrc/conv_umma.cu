@@ -24,6 +24,7 @@
 // The double-buffered accumulator lets tile i's epilogue overlap tile i+1's MMAs.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "decode_math.cuh"
 
 #include <cuda.h>  // CUtensorMap + enums only; entry points are fetched at run time
 #include <string.h>
@@ -49,7 +50,99 @@ struct ConvKernelParams {
   const __nv_bfloat16* res;
   int ld_out, ld_res;
   int leaky, out_f32, upsample;
+  // DECODE epilogue (YOLO head: 3 anchors x (5 + 80) channels): candidates instead of logits
+  float anchor_w[3], anchor_h[3];
+  float train_w, train_h;
+  float prob_thresh;
+  int box_offset;
+  const int* orig_hw;
+  uint4* cands;   // y3_cand records, [N][cap]
+  int* counts;    // [N]
+  int cap;
 };
+
+// One anchor of the fused YOLO-head epilogue.  The thread's pixel has its 255 logits in TMEM lane
+// `taddr`; anchor A's fields are columns [85 A, 85 A + 85).  Two passes over the same columns
+// (TMEM re-reads are cheap): arg-max of the 80 class logits (first maximum wins, like torch.max),
+// then the softmax denominator sum(exp(v - max)) in ascending class order.
+template <int A>
+__device__ __forceinline__ void decode_anchor(uint32_t taddr, const ConvKernelParams& p, float (&t)[5], float& sum,
+                                              int& cls) {
+  constexpr int BASE = 85 * A, C0 = BASE / 16, C1 = (BASE + 84) / 16;
+  float best = -INFINITY;
+  int best_idx = 0;
+#pragma unroll
+  for (int c = C0; c <= C1; ++c) {
+    uint32_t v[16];
+    ptx::tmem_ld_x16(taddr + 16 * c, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 16 * c) + q);
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int f = 16 * c + 4 * q + e - BASE;  // compile-time
+        if (f < 0 || f >= 85) continue;
+        const float x = __uint_as_float(v[4 * q + e]) + bb[e];
+        if (f < 5) t[f < 5 ? f : 0] = x;
+        else if (x > best) { best = x; best_idx = f - 5; }
+      }
+    }
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int c = C0; c <= C1; ++c) {
+    uint32_t v[16];
+    ptx::tmem_ld_x16(taddr + 16 * c, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + 16 * c) + q);
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int f = 16 * c + 4 * q + e - BASE;
+        if (f < 5 || f >= 85) continue;
+        acc += expf((__uint_as_float(v[4 * q + e]) + bb[e]) - best);
+      }
+    }
+  }
+  sum = acc;
+  cls = best_idx;
+}
+
+// Threshold + box math + warp-aggregated append to the per-image candidate lists (lanes of one warp
+// may sit in two images when the tile straddles an image boundary).
+__device__ __forceinline__ void emit_cand(const ConvKernelParams& p, int a, bool valid, int img, int row, int col,
+                                          const float (&t)[5], float sum, int cls, int lane) {
+  // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)  (darknet.py:104-108)
+  const float prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(t[4]));
+  const bool pass = valid && prob >= p.prob_thresh;  // inference.py:342
+  uint32_t mask = __ballot_sync(0xffffffffu, pass);
+  while (mask) {
+    const int leader = __ffs(mask) - 1;
+    const int li = __shfl_sync(0xffffffffu, img, leader);
+    const uint32_t same = __ballot_sync(0xffffffffu, pass && img == li);
+    int base = 0;
+    if (lane == leader) base = atomicAdd(p.counts + li, __popc(same));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass && img == li) {
+      const int slot = base + __popc(same & ((1u << lane) - 1u));
+      if (slot < p.cap) {
+        uint4 lo, hi;
+        const int cell = row * p.Wo + col;
+        make_cand(t[0], t[1], t[2], t[3], prob, cls, p.box_offset + a * p.HoWo + cell, row, col, p.Ho, p.Wo,
+                  p.anchor_w[a], p.anchor_h[a], p.train_w, p.train_h, (float)p.orig_hw[2 * img],
+                  (float)p.orig_hw[2 * img + 1], lo, hi);
+        uint4* dst = p.cands + 2 * ((long long)img * p.cap + slot);
+        dst[0] = lo;
+        dst[1] = hi;
+      }
+    }
+    mask &= ~same;
+  }
+}
 
 // CG = 1: one CTA per tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) shares one
 // 256-row tile — each CTA stages its own 128 rows of A and HALF of the weight slab, the leader's
@@ -94,7 +187,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t 
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
 }
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r,
@@ -325,6 +418,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      } else if constexpr (DECODE) {
+        // ---- YOLO head: decode the pixel's three anchors straight from the accumulator ----
+        const bool valid = m < p.M;
+        const int mm = valid ? m : 0;
+        const int img = mm / p.HoWo;
+        const int rem = mm - img * p.HoWo;
+        const int grow = rem / p.Wo;
+        const int gcol = rem - grow * p.Wo;
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        float t[5], sum;
+        int cls;
+        decode_anchor<0>(taddr, p, t, sum, cls);
+        emit_cand(p, 0, valid, img, grow, gcol, t, sum, cls, lane);
+        decode_anchor<1>(taddr, p, t, sum, cls);
+        emit_cand(p, 1, valid, img, grow, gcol, t, sum, cls, lane);
+        decode_anchor<2>(taddr, p, t, sum, cls);
+        emit_cand(p, 2, valid, img, grow, gcol, t, sum, cls, lane);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
       } else {
         // ---- direct: registers -> global, one output row per thread ----
         const bool valid = m < p.M;
@@ -526,9 +640,19 @@ static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x,
   return Y3_OK;
 }
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
+struct DecodeArgs {
+  const y3_head_desc* head;
+  float prob_thresh;
+  const int* orig_hw;
+  void* cands;
+  int* counts;
+  int cap;
+};
+
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false>
 static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
-                       const void* residual, void* y, cudaStream_t stream, int force_im2col) {
+                       const void* residual, void* y, cudaStream_t stream, int force_im2col,
+                       const DecodeArgs* dec = nullptr) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG>;
   const int ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
@@ -550,6 +674,19 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.ld_out = d->ld_y; p.ld_res = d->ld_res;
   p.leaky = d->leaky; p.out_f32 = d->out_f32; p.upsample = d->upsample2x;
+  p.orig_hw = nullptr; p.cands = nullptr; p.counts = nullptr; p.cap = 0;
+  p.train_w = p.train_h = 1.f; p.prob_thresh = 0.f; p.box_offset = 0;
+  for (int a = 0; a < 3; ++a) p.anchor_w[a] = p.anchor_h[a] = 0.f;
+  if (DECODE) {
+    for (int a = 0; a < 3; ++a) { p.anchor_w[a] = dec->head->anchor_w[a]; p.anchor_h[a] = dec->head->anchor_h[a]; }
+    p.train_w = dec->head->train_w; p.train_h = dec->head->train_h;
+    p.prob_thresh = dec->prob_thresh;
+    p.box_offset = dec->head->box_offset;
+    p.orig_hw = dec->orig_hw;
+    p.cands = reinterpret_cast<uint4*>(dec->cands);
+    p.counts = dec->counts;
+    p.cap = dec->cap;
+  }
 
   int rc = resolve_driver_entry_points();
   if (rc != Y3_OK) return rc;
@@ -580,7 +717,7 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
     }
   }
 
-  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED, CG>;
+  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED, CG, DECODE>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     Y3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -662,6 +799,28 @@ static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, cons
 }
 
 }  // namespace y3
+
+extern "C" int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
+                                   const y3_head_desc* head, float prob_thresh, const int32_t* orig_hw,
+                                   y3_cand* cands, int32_t* counts, int32_t cap, void* stream) {
+  using namespace y3;
+  Y3_CHECK_ARG(d && x && w && bias && head && orig_hw && cands && counts && cap > 0, "conv2d_yolo_head: null argument");
+  Y3_CHECK_ARG(d->ksize == 1 && d->stride == 1 && d->pad == 0, "conv2d_yolo_head: the head convolution must be 1x1/1");
+  Y3_CHECK_ARG(d->cout == 256 && d->cin % 64 == 0 && d->ld_x >= d->cin && d->ld_x % 8 == 0,
+               "conv2d_yolo_head: cout=%d (256 stored channels required), cin=%d (multiple of 64 required)", d->cout,
+               d->cin);
+  Y3_CHECK_ARG(head->num_anchors == 3 && head->num_classes == 80,
+               "conv2d_yolo_head: %d anchors x %d classes (3 x 80 required; use y3_conv2d + y3_yolo_decode_cands)",
+               head->num_anchors, head->num_classes);
+  Y3_CHECK_ARG(head->n == d->n && head->g_h == d->h && head->g_w == d->w, "conv2d_yolo_head: head / conv shapes differ");
+  Y3_CHECK_ARG(!d->leaky && !d->upsample2x, "conv2d_yolo_head: the head convolution is linear");
+  Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(cands) & 15) == 0,
+               "conv2d_yolo_head: pointers must be 16-byte aligned");
+  DecodeArgs dec = {head, prob_thresh, orig_hw, cands, counts, cap};
+  return launch_conv<256, 64, false, 1, true>(d, x, w, bias, nullptr, const_cast<float*>(bias) /*unused*/,
+                                              reinterpret_cast<cudaStream_t>(stream), 0, &dec);
+}
 
 extern "C" int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                          const void* residual, void* y, void* stream) {

@@ -8,6 +8,7 @@
 // /train size, *image size) with explicit round-to-nearest intrinsics so no FMA contraction
 // changes a rounding; only sigmoid/exp themselves may differ from torch's by an ulp.
 #include "common.cuh"
+#include "decode_math.cuh"
 
 namespace y3 {
 
@@ -15,10 +16,6 @@ struct BoxOut {
   float x, y, w, h, prob;
   int cls;
 };
-
-__device__ __forceinline__ float sigmoidf_ref(float v) {
-  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
-}
 
 // Whole warp cooperates; result valid in every lane.
 __device__ __forceinline__ BoxOut decode_box(const y3_head_desc& d, const float* __restrict__ logits,
@@ -65,11 +62,6 @@ __device__ __forceinline__ BoxOut decode_box(const y3_head_desc& d, const float*
   o.prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
   o.cls = best_idx;
   return o;
-}
-
-__device__ __forceinline__ int f2i_trunc(float v) {
-  // numpy astype(int) truncates toward zero; values stay far inside int32 for any sane logit
-  return __float2int_rz(v);
 }
 
 __device__ __forceinline__ bool next_box(const y3_head_desc& d, long long wid, int& img, int& a,
@@ -198,19 +190,12 @@ decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
     // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)  (darknet.py:104-108)
     const float prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
     if (prob >= prob_thresh) {  // inference.py:342
-      const float oh = (float)orig_hw[2 * img], ow = (float)orig_hw[2 * img + 1];
-      const float x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)d.g_w);
-      const float y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)d.g_h);
-      const float w = __fdiv_rn(__fmul_rn(expf(tw), d.anchor_w[a]), d.train_w);
-      const float h = __fdiv_rn(__fmul_rn(expf(th), d.anchor_h[a]), d.train_h);
-      const int cx = f2i_trunc(__fmul_rn(x, ow));  // inference.py:351-353
-      const int cy = f2i_trunc(__fmul_rn(y, oh));
-      const int bw = f2i_trunc(__fmul_rn(w, ow));
-      const int bh = f2i_trunc(__fmul_rn(h, oh));
-      const int hw = bw >> 1, hh = bh >> 1;  // cxywh_to_tlbr: c -/+ wh // 2 (wh >= 0)
+      uint4 rlo, rhi;
+      make_cand(tx, ty, tw, th, prob, cls, d.box_offset + m, row, col, d.g_h, d.g_w, d.anchor_w[a], d.anchor_h[a],
+                d.train_w, d.train_h, (float)orig_hw[2 * img], (float)orig_hw[2 * img + 1], rlo, rhi);
       const int slot = atomicAdd(&s_count, 1);
-      s_rec[slot][0] = make_uint4((uint32_t)(cx - hw), (uint32_t)(cy - hh), (uint32_t)(cx + hw), (uint32_t)(cy + hh));
-      s_rec[slot][1] = make_uint4(__float_as_uint(prob), (uint32_t)cls, (uint32_t)(d.box_offset + m), 0u);
+      s_rec[slot][0] = rlo;
+      s_rec[slot][1] = rhi;
     }
   }
   __syncthreads();

@@ -19,12 +19,12 @@ LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
 # Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
 EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
-    "y3_conv2d", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
+    "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
 )
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ConvDesc(ctypes.Structure):
@@ -68,6 +68,8 @@ def lib():
     L.y3_launch_count.restype = c_longlong
     L.y3_reset_launch_count.restype = None
     L.y3_conv2d.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.y3_conv2d_yolo_head.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(HeadDesc), c_float,
+                                      c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     L.y3_conv_chain_stem_u8.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
     L.y3_conv_chain_res64.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
     L.y3_maxpool.argtypes = [c_void_p, c_void_p] + [c_int32] * 8 + [c_void_p]
@@ -145,6 +147,13 @@ def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, 
     d = ConvDesc(n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, ld_res, int(leaky), int(out_f32),
                  int(upsample2x), (1 if force_im2col else 0) | (2 if force_direct else 0) | (4 if force_1cta else 0))
     _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
+
+
+def conv2d_yolo_head(x_ptr, w, bias, head, prob_thresh, orig_hw, cands, counts, cap, *, n, h, w_in, cin, ld_x):
+    """1x1 YOLO head convolution with decode + threshold + candidate append fused into its epilogue."""
+    d = ConvDesc(n, h, w_in, cin, 256, 1, 1, 0, ld_x, 256, 0, 0, 0, 0, 0)
+    _check(lib().y3_conv2d_yolo_head(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), ctypes.byref(head),
+                                     float(prob_thresh), _ptr(orig_hw), _ptr(cands), _ptr(counts), cap, _stream()))
 
 
 def conv_chain_stem_u8(img, w1, b1, w2, b2, y_ptr, *, ld_y, leaky1=True, leaky2=True):

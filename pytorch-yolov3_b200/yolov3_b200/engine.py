@@ -206,6 +206,9 @@ class Engine:
             self.op_groups.append(group)
 
         use_chain = os.environ.get("Y3_NO_CHAIN", "0") != "1"
+        use_fused_decode = os.environ.get("Y3_NO_FUSED_DECODE", "0") != "1"
+        self.num_fused_heads = 0
+        self._prob_thresh = 0.0
 
         def conv_geom(j):
             bj = blocks[j]
@@ -289,7 +292,17 @@ class Engine:
                           upsample2x=up)
                 fn = (lambda xp=xin.ptr, w=w, bias=bias, yp=yv.ptr, kw=kw: _lib.conv2d(xp, w, bias, yp, **kw))
                 in_stem = stem_ok and i in (0, 1)
-                emit(f"conv{i}", fn, "stem_unfused" if in_stem else None)
+                # YOLO head with 3 anchors x 80 classes: the detection programs decode in the conv epilogue
+                yb = blocks[i + 1] if head else None
+                fuse_head = (head and use_fused_decode and k == 1 and s == 1 and xin.C % 64 == 0 and cout == 255
+                             and len(yb["mask"]) == 3 and yb["classes"] == 80)
+                emit(f"conv{i}", fn, "stem_unfused" if in_stem else ("head_logits" if fuse_head else None))
+                if fuse_head:
+                    hfn = (lambda xp=xin.ptr, w=w, bias=bias, hk=len(heads), h=xin.H, wi=xin.W, c=xin.C, lx=xin.ld:
+                           _lib.conv2d_yolo_head(xp, w, bias, self.head_descs[hk][0], self._prob_thresh, self.orig_hw,
+                                                 self.cands, self.counts, self.cap, n=B, h=h, w_in=wi, cin=c, ld_x=lx))
+                    emit(f"headconv{i}", hfn, "head_fused")
+                    self.num_fused_heads += 1
                 ho, wo = shape[i][1], shape[i][2]
                 cin_real = cin0 if inputs_of(i)[0] == INPUT else shape[inputs_of(i)[0]][0]
                 flops = 2 * B * ho * wo * cout * cin_real * k * k
@@ -297,7 +310,7 @@ class Engine:
                 if in_stem:
                     self.conv_ops_unfused_stem.append((i, fn, flops))
                 else:
-                    self.conv_ops.append((i, fn, flops))
+                    self.conv_ops.append((i, hfn if fuse_head else fn, flops))
                 if in_stem and i == 1:
                     (w1, b1), (w2, b2) = self._stem_w0, (w, bias)
                     sfn = (lambda w1=w1, b1=b1, w2=w2, b2=b2, yp=yv.ptr, ly=yv.ld,
@@ -380,6 +393,8 @@ class Engine:
         if not heads:
             raise RuntimeError("cfg has no [yolo] block")
         self.head_descs = []
+        fused_names = {n for n, g_ in zip(self.op_names, self.op_groups) if g_ == "head_fused"}
+        self.head_fused = [f"headconv{y - 1}" in fused_names for y, _ in heads]
         off = 0
         M = sum(len(blocks[y]["mask"]) * v.H * v.W for y, v in heads)
         classes = None
@@ -461,23 +476,42 @@ class Engine:
     # ------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------
-    def run_backbone(self, fused_stem=False):
+    def run_backbone(self, fused_stem=False, fused_heads=False):
         """All block launches in order.  Blocks 0-1 exist in two forms when the plan has a stem:
         separate convolutions over the packed input buffer (float32 input), or the fused
-        uint8-image kernel (`fused_stem`, uint8 programs — no packing launch needed)."""
-        skip = "stem_unfused" if (fused_stem and self.stem is not None) else "stem_fused"
+        uint8-image kernel (`fused_stem`, uint8 programs — no packing launch needed).  YOLO head
+        convolutions exist in two forms as well: float32 logits for `Darknet.forward`, or
+        (`fused_heads`, detection programs) decode + threshold + candidate append in the epilogue —
+        the caller zeroes `counts` and sets `_prob_thresh` first."""
+        skip = {"stem_unfused" if (fused_stem and self.stem is not None) else "stem_fused",
+                "head_logits" if fused_heads else "head_fused"}
         for op, group in zip(self.backbone_ops, self.op_groups):
-            if group != skip:
+            if group not in skip:
                 op()
 
     def _decode_dense(self):
         for d, logits in self.head_descs:
             _lib.yolo_decode_dense(d, logits, self.bbox, self.prob, self.cidx)
 
+    def _detect(self, prob_thresh, iou_thresh, compact=True, fused_stem=False):
+        """Backbone + decode + NMS (+ compaction).  Heads that can decode in their epilogue do; the
+        others (other class / anchor counts) write logits and run the stand-alone decode kernel."""
+        self.counts.zero_()
+        self._prob_thresh = float(prob_thresh)
+        self.run_backbone(fused_stem=fused_stem, fused_heads=True)
+        for hk, (d, logits) in enumerate(self.head_descs):
+            if not self.head_fused[hk]:
+                _lib.yolo_decode_cands(d, logits, prob_thresh, self.orig_hw, self.cands, self.counts, self.cap)
+        self._nms_tail(iou_thresh, compact)
+
     def _detect_tail(self, prob_thresh, iou_thresh, compact=True):
+        """Decode (stand-alone kernels, from the logits of a previous run_backbone()) + NMS."""
         self.counts.zero_()
         for d, logits in self.head_descs:
             _lib.yolo_decode_cands(d, logits, prob_thresh, self.orig_hw, self.cands, self.counts, self.cap)
+        self._nms_tail(iou_thresh, compact)
+
+    def _nms_tail(self, iou_thresh, compact=True):
         _lib.nms(self.cands, self.counts, self.B, self.cap, self.num_classes, iou_thresh, 1, self.sorted, self.keep,
                  self.first_box, self.nms_ws, class_start=self.class_start, class_kept=self.class_kept)
         if compact:  # flat y3_cand records (device-resident result; bench / multi-GPU gather)
@@ -502,19 +536,16 @@ class Engine:
             def fn():
                 if self.stem is None:
                     pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self.run_backbone(fused_stem=True)
-                self._detect_tail(key[1], key[2])
+                self._detect(key[1], key[2], fused_stem=True)
         elif kind == "nms_u8":  # inference(): final arrays are emitted by a second launch (Engine.emit)
             def fn():
                 if self.stem is None:
                     pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self.run_backbone(fused_stem=True)
-                self._detect_tail(key[1], key[2], compact=False)
+                self._detect(key[1], key[2], compact=False, fused_stem=True)
         elif kind == "det_f32":
             def fn():
                 pack_f32(self.in_f32, self.in_view.buf, self.in_view.C)
-                self.run_backbone()
-                self._detect_tail(key[1], key[2])
+                self._detect(key[1], key[2])
         else:
             raise KeyError(kind)
         return fn

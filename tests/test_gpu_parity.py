@@ -323,8 +323,15 @@ def test_micro_network_teacher_forced_convs(micro):
         assert rel_err(got, ref) <= CONV_TOL, (i, rel_err(got, ref))
 
 
-def oracle_tail_from_engine_logits(net, eng, orig_shapes, prob_thresh, iou):
-    """Decode + post-process + NMS on the CPU oracle from the engine's OWN head logits."""
+def oracle_tail_from_engine_logits(net, eng, orig_shapes, prob_thresh, iou, imgs=None):
+    """Decode + post-process + NMS on the CPU oracle from the engine's OWN head logits.  Heads that
+    decode inside the convolution epilogue never write their logits: pass the images and the
+    float-input program (same kernels, same accumulators — test_uint8_stem_program_equals_float_program)
+    is run on the same pixels to materialise them."""
+    if eng.num_fused_heads:
+        assert imgs is not None
+        net.forward(torch.from_numpy(PO.preprocess(list(imgs))).to(dev()))
+        torch.cuda.synchronize()
     boxes, probs, idxs = [], [], []
     yolo_blocks = [b for b in net.blocks if b["type"] == "yolo"]
     for (d, logits), yb in zip(eng.head_descs, yolo_blocks):
@@ -506,7 +513,7 @@ def test_yolov3_416_tail_exact_and_candidates_nonempty(yolov3_full):
     imgs = [rng.integers(0, 256, (416, 416, 3), dtype=np.uint8) for _ in range(2)]
     res = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, nms_iou_thresh=0.3, resize=False)
     eng = net.engine(2, 416, 416)
-    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3)
+    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3, imgs)
     equal, bad, tot = compare_detection_lists(res, want)
     print(f"yolov3@416 tail: {equal}/2 images identical incl. order, {bad} of {tot} detections differ")
     assert tot > 1000  # calibrated weights give thousands of candidates (F8)
@@ -552,7 +559,7 @@ def test_yolov3_tiny_416_end_to_end(tmp_path_factory):
     imgs = [rng.integers(0, 256, (416, 416, 3), dtype=np.uint8)]
     res = yolov3_b200.inference(net, imgs, device="cuda:0", prob_thresh=0.05, nms_iou_thresh=0.3, resize=False)
     eng = net.engine(1, 416, 416)
-    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3)
+    *_, want = oracle_tail_from_engine_logits(net, eng, [im.shape for im in imgs], 0.05, 0.3, imgs)
     equal, bad, tot = compare_detection_lists(res, want)
     assert bad <= max(2, 0.002 * tot)
     with torch.no_grad():
@@ -657,10 +664,60 @@ def test_uint8_stem_program_equals_float_program(yolov3_full):
     net.forward(torch.from_numpy(PO.preprocess(list(imgs))).to(dev()))
     torch.cuda.synchronize()
     want = [logits.clone() for _, logits in eng.head_descs]
-    yolov3_b200.inference(net, list(imgs), device="cuda:0", prob_thresh=0.05, resize=False)
+    for _, logits in eng.head_descs:
+        logits.zero_()
+    # uint8 program with logits-writing heads (the fused-decode heads are the other form of the same convs)
+    eng.in_u8.copy_(torch.from_numpy(imgs).to(dev()))
+    eng.run_backbone(fused_stem=True, fused_heads=False)
     torch.cuda.synchronize()
     for (_, logits), w in zip(eng.head_descs, want):
         assert torch.equal(logits, w)
+
+
+def test_fused_head_decode_equals_standalone_decode(yolov3_full):
+    """Candidates appended by the head convolutions' decode epilogue vs y3_yolo_decode_cands on the
+    logits of the same pixels: same boxes / classes / box indices; probabilities within 2e-6
+    (different summation order of the softmax denominator); membership may differ only for
+    probabilities within that distance of the threshold."""
+    net, *_ = yolov3_full
+    rng = np.random.default_rng(17)
+    imgs = rng.integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
+    eng = net.engine(2, 416, 416)
+    assert eng.num_fused_heads == 3 and all(eng.head_fused)
+    thr = 0.05
+    eng.in_u8.copy_(torch.from_numpy(imgs).to(dev()))
+    eng.orig_hw.copy_(torch.tensor([[416, 416]] * 2, dtype=torch.int32))
+
+    def snapshot():
+        torch.cuda.synchronize()
+        out = []
+        counts = eng.counts.cpu().numpy()
+        cands = eng.cands.cpu().numpy()
+        for i in range(2):
+            rec = cands[i, :counts[i]]
+            out.append({int(r[6]): (tuple(int(v) for v in r[:4]), float(r[4:5].view(np.float32)[0]), int(r[5])) for r in rec})
+        return out
+
+    eng.counts.zero_()
+    eng._prob_thresh = thr
+    eng.run_backbone(fused_stem=True, fused_heads=True)
+    fused = snapshot()
+    eng.run_backbone(fused_stem=True, fused_heads=False)
+    eng._detect_tail(thr, 0.3)
+    plain = snapshot()
+    total = edge = 0
+    for f, p in zip(fused, plain):
+        assert len(p) > 1000
+        for box in set(f) | set(p):
+            total += 1
+            if box in f and box in p:
+                assert f[box][0] == p[box][0] and f[box][2] == p[box][2], (box, f[box], p[box])
+                assert abs(f[box][1] - p[box][1]) <= 2e-6 * p[box][1]
+            else:
+                prob = (f.get(box) or p.get(box))[1]
+                assert abs(prob - thr) <= 4e-6 * thr, (box, prob)
+                edge += 1
+    print(f"fused head decode: {total} candidates, {edge} threshold-edge membership differences")
 
 
 def test_first_layer_im2col_packing_matches_unfold():

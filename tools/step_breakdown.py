@@ -65,7 +65,8 @@ def main():
             ("nms", nms), ("compact", compact),
             ("backbone + decode", lambda: (eng.run_backbone(fused_stem=True), decode())),
             ("backbone + decode + nms", lambda: (eng.run_backbone(fused_stem=True), decode(), nms())),
-            ("whole step", lambda: (eng.run_backbone(fused_stem=True), eng._detect_tail(bench.PROB_THRESH, bench.IOU_THRESH)))]
+            ("whole step, stand-alone decode", lambda: (eng.run_backbone(fused_stem=True), eng._detect_tail(bench.PROB_THRESH, bench.IOU_THRESH))),
+            ("whole step (fused head decode)", lambda: eng._detect(bench.PROB_THRESH, bench.IOU_THRESH, fused_stem=True))]
     for name, fn in rows:
         print(f"{name:28s} {timed(fn, s):8.3f} ms")
     print("candidates", int(eng.counts.sum()), "kept", int(eng.det_counts.sum()))
