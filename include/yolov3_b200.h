@@ -51,6 +51,13 @@ int y3_check_device(int dev);
 long long y3_launch_count(void);
 void y3_reset_launch_count(void);
 
+/* ---- a12: host-side staging of the image batch ---------------------------------------- */
+/* np.stack(images) of yolov3/inference.py:332 as n plain memcpy's into one (pinned) staging buffer,
+ * spread over up to `threads` host threads; the caller holds no interpreter lock meanwhile.
+ * Host memory only; no CUDA call. */
+int y3_stage_images(void* dst, const void* const* srcs, int32_t n, int64_t bytes_each,
+                    int32_t threads);
+
 /* ---- a5/a8/a9: convolutional block ------------------------------------- */
 /*
  * One Darknet [convolutional] block: Conv2d -> BatchNorm2d(eval) -> LeakyReLU

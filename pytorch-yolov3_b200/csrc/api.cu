@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 namespace y3 {
 
 static thread_local char g_err[512] = "";
@@ -59,6 +62,26 @@ int y3_check_device(int dev) {
                   dev, major, minor);
     return Y3_EARCH;
   }
+  return Y3_OK;
+}
+
+int y3_stage_images(void* dst, const void* const* srcs, int32_t n, int64_t bytes_each, int32_t threads) {
+  Y3_CHECK_ARG(dst && srcs && n > 0 && bytes_each > 0, "stage_images: bad arguments");
+  for (int i = 0; i < n; ++i) Y3_CHECK_ARG(srcs[i] != nullptr, "stage_images: image %d is null", i);
+  const long long total = (long long)n * bytes_each;
+  int t = threads < 1 ? 1 : (threads > 16 ? 16 : threads);
+  const long long by_size = total >> 21;  // a thread is worth starting for ~2 MB of copying
+  if (t > by_size) t = by_size < 1 ? 1 : (int)by_size;
+  if (t > n) t = n;
+  auto work = [=](int w) {
+    for (int i = w; i < n; i += t) memcpy(static_cast<char*>(dst) + (long long)i * bytes_each, srcs[i], (size_t)bytes_each);
+  };
+  if (t == 1) { work(0); return Y3_OK; }
+  std::vector<std::thread> pool;
+  pool.reserve(t - 1);
+  for (int w = 1; w < t; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& th : pool) th.join();
   return Y3_OK;
 }
 

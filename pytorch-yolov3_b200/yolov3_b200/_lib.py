@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
 # Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
 EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
-    "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
+    "y3_stage_images", "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
 )
@@ -67,6 +67,7 @@ def lib():
     L.y3_check_device.argtypes = [ctypes.c_int]
     L.y3_launch_count.restype = c_longlong
     L.y3_reset_launch_count.restype = None
+    L.y3_stage_images.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32]
     L.y3_conv2d.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.y3_conv2d_yolo_head.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(HeadDesc), c_float,
                                       c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
@@ -137,6 +138,14 @@ def launch_count():
 
 def reset_launch_count():
     lib().y3_reset_launch_count()
+
+
+def stage_images(dst, images, threads):
+    """``np.stack(images)`` into ``dst`` (host array, e.g. a pinned staging buffer) by the library's
+    host threads; ``images`` are equally shaped C-contiguous uint8 arrays."""
+    n = len(images)
+    ptrs = (c_void_p * n)(*[im.ctypes.data for im in images])
+    _check(lib().y3_stage_images(dst.ctypes.data, ptrs, n, images[0].nbytes, threads))
 
 
 # ---- kernels --------------------------------------------------------------------------------

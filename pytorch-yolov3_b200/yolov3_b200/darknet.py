@@ -220,6 +220,7 @@ class Darknet(torch.nn.Module):
     def invalidate(self):
         """Drop compiled plans (call after editing parameters in place)."""
         self._engines.clear()
+        self.__dict__.pop("_host_io", None)  # inference()'s staging buffers hold plans too
         self._weights_version += 1
 
     # -- execution ------------------------------------------------------------------------------
@@ -231,9 +232,11 @@ class Darknet(torch.nn.Module):
                 dev = p.device
         return _lib.require_device(dev)
 
-    def engine(self, batch, height, width):
-        """The compiled execution plan for this input geometry (built on first use)."""
-        key = (batch, height, width)
+    def engine(self, batch, height, width, slot=0):
+        """The compiled execution plan for this input geometry (built on first use).  ``slot`` > 0
+        gives further independent instances (own buffers and graphs) of the same geometry:
+        ``inference`` pipelines sub-batches through several of them."""
+        key = (batch, height, width) if slot == 0 else (batch, height, width, slot)
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self, batch, height, width, self._target_device())

@@ -78,3 +78,48 @@ def gather_detections(rec, counts, group=None, device=None):
     out_cnt = np.concatenate([c.cpu().numpy()[:metas[r, 0]] for r, c in enumerate(all_cnt)])
     out_rec = np.concatenate([t.cpu().numpy()[:metas[r, 1]] for r, t in enumerate(all_rec)])
     return out_rec, out_cnt
+
+
+def gather_outputs(tlbr, prob, cls, per_image, group=None, dst=0):
+    """Gather the final detection arrays of every rank on rank ``dst`` WITHOUT a host round trip.
+
+    ``tlbr`` int64 [K,4], ``prob`` float32 [K], ``cls`` int64 [K] are this rank's detections, images
+    back to back (``Engine.out_tlbr[:K]`` etc. after ``inference()``), ``per_image`` the detections
+    per local image.  The tensors stay where they live (``cuda:<local_rank>`` under NCCL, CPU under
+    gloo): one ``all_gather`` of the counts, then one ``gather`` per array, padded to the largest
+    rank.  Returns on ``dst``: ``(list of (tlbr, prob, cls) per rank — views of the gathered buffers,
+    per-image counts int64 numpy [B_total])``; on the other ranks ``(None, counts)``.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    device = tlbr.device
+    cnt = torch.as_tensor(np.asarray(per_image, dtype=np.int64)).to(device)
+    meta = torch.tensor([cnt.numel(), int(prob.shape[0])], dtype=torch.int64, device=device)
+    metas = torch.zeros(world * 2, dtype=torch.int64, device=device)  # flat: gloo accepts no other shape
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas = metas.cpu().numpy().reshape(world, 2)
+    max_img, max_rec = max(int(metas[:, 0].max()), 1), max(int(metas[:, 1].max()), 1)
+    cnt_pad = torch.zeros(max_img, dtype=torch.int64, device=device)
+    cnt_pad[:cnt.numel()] = cnt
+    all_cnt = torch.zeros(world * max_img, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_cnt, cnt_pad, group=group)
+    all_cnt = all_cnt.cpu().numpy().reshape(world, max_img)
+    counts = np.concatenate([all_cnt[r, :metas[r, 0]] for r in range(world)])
+
+    def padded(t, shape):
+        if t.shape[0] == shape[0]:
+            return t.contiguous()
+        out = torch.zeros(shape, dtype=t.dtype, device=device)
+        out[:t.shape[0]] = t
+        return out
+
+    parts = []
+    for t, shape in ((tlbr, (max_rec, 4)), (prob, (max_rec,)), (cls, (max_rec,))):
+        src = padded(t, shape)
+        bufs = [torch.empty_like(src) for _ in range(world)] if rank == dst else None
+        dist.gather(src, bufs, dst=dst, group=group)
+        parts.append(bufs)
+    if rank != dst:
+        return None, counts
+    per_rank = [(parts[0][r][:metas[r, 1]], parts[1][r][:metas[r, 1]], parts[2][r][:metas[r, 1]]) for r in range(world)]
+    return per_rank, counts

@@ -517,11 +517,13 @@ class Engine:
         if compact:  # flat y3_cand records (device-resident result; bench / multi-GPU gather)
             _lib.compact_kept(self.sorted, self.keep, self.counts, self.B, self.cap, self.dets, self.det_counts, 1)
 
-    def emit(self):
+    def emit(self, out=None):
         """Second, tiny launch of `inference`: write the kept records as the reference's final arrays
-        at the per-class-group positions the host put into ``dst_off``."""
+        at the per-class-group positions the host put into ``dst_off`` — into this plan's own
+        output buffers, or into ``out = (tlbr, prob, cls)`` shared by the sub-batches of one call."""
+        tlbr, prob, cls = out if out is not None else (self.out_tlbr, self.out_prob, self.out_cls)
         _lib.emit_detections(self.sorted, self.keep, self.class_start, self.dst_off, self.B, self.cap,
-                             self.num_classes, self.out_tlbr, self.out_prob, self.out_cls)
+                             self.num_classes, tlbr, prob, cls)
 
     def _program(self, key):
         kind = key[0]

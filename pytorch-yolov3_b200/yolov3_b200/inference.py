@@ -10,10 +10,15 @@ images up (pinned memory), reads back how many detections every (image, class) g
 the device where each group goes (class groups follow the reference's ``set(class_idx)`` visiting
 order) and receives the final int64 / float32 arrays.  There is no CPU implementation here.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
 from . import _lib
+
+_TRACE = os.environ.get("Y3_TRACE", "0") == "1"
 
 
 def cxywh_to_tlbr(bbox_xywh):
@@ -84,35 +89,11 @@ def _pinned(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
-_copy_pool = None
-
-
 def _stack_into(dst, images):
-    """``np.stack(images)`` straight into the pinned staging buffer; large batches are copied by a
-    few threads (NumPy releases the GIL for contiguous copies)."""
-    global _copy_pool
-    first = images[0].shape
-    for im in images:
-        if im.shape != first:  # the reference fails in np.stack with this error type
-            raise ValueError("all input arrays must have the same shape")
-        if im.dtype != np.uint8:
-            raise ValueError(f"images must be uint8, got {im.dtype}")
-    n = len(images)
-    if n < 8:
-        for i, im in enumerate(images):
-            dst[i] = im
-        return
-    if _copy_pool is None:
-        import os
-        from concurrent.futures import ThreadPoolExecutor
-        _copy_pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
-    workers = _copy_pool._max_workers
-
-    def job(lo):
-        for i in range(lo, n, workers):
-            dst[i] = images[i]
-
-    list(_copy_pool.map(job, range(workers)))
+    """``np.stack(images)`` straight into the pinned staging buffer: plain memcpy's on a few host
+    threads of the library (no interpreter lock held); non-contiguous inputs are compacted first."""
+    images = [im if im.flags.c_contiguous else np.ascontiguousarray(im) for im in images]
+    _lib.stage_images(dst, images, min(16, os.cpu_count() or 1))
 
 
 def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True):
@@ -131,6 +112,7 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
         list (one entry per image) of ``[bbox_tlbr int64 (K,4), class_prob float32 (K,),
         class_idx int64 (K,)]`` in ORIGINAL-image pixels, unclipped, ordered like the reference.
     """
+    t_enter = time.perf_counter()
     if not isinstance(images, list):
         images = [images]
     dev = _lib.require_device(device)
@@ -142,51 +124,131 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
     if images[0].ndim != 3 or images[0].shape[2] != 3:
         raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got shape {images[0].shape}")
     B, (H, W, _) = len(images), images[0].shape
-    eng = net.engine(B, H, W)
-    if eng.device != dev:
-        raise RuntimeError(f"net runs on {eng.device}, inference(device='{device}') requested")
+    first = images[0].shape
+    for im in images:
+        if im.shape != first:  # the reference fails in np.stack with this error type
+            raise ValueError("all input arrays must have the same shape")
+        if im.dtype != np.uint8:
+            raise ValueError(f"images must be uint8, got {im.dtype}")
 
-    C = eng.num_classes
+    # Large batches go through the GPU as a few sub-batches on their own streams and plans: while
+    # sub-batch k computes, the host stages and uploads k+1 and finishes k-1 (destinations, emit,
+    # download) — the synchronous call hides most of its own host and PCIe time.
+    spans = _sub_batches(B)
+    io = net.__dict__.setdefault("_host_io", {}).get((B, H, W, str(dev)))
+    if io is None:
+        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if len(spans) > 1 else 0)
+        if eng0.device != dev:
+            raise RuntimeError(f"net runs on {eng0.device}, inference(device='{device}') requested")
+        with torch.cuda.device(dev):
+            C, M = eng0.num_classes, eng0.M
+            io = {"img": _pinned((B, H, W, 3), torch.uint8), "hw": _pinned((B, 2), torch.int32),
+                  "meta": [_pinned((2, hi - lo, C), torch.int32) for lo, hi in spans],
+                  "dst": [_pinned((hi - lo, C), torch.int32) for lo, hi in spans],
+                  "engines": [net.engine(hi - lo, H, W, slot=(k + 1) if len(spans) > 1 else 0)
+                              for k, (lo, hi) in enumerate(spans)],
+                  "streams": [torch.cuda.Stream(device=dev) for _ in spans] if len(spans) > 1 else [None],
+                  "out": (torch.empty(B * M, 4, device=dev, dtype=torch.int64),
+                          torch.empty(B * M, device=dev, dtype=torch.float32),
+                          torch.empty(B * M, device=dev, dtype=torch.int64)) if len(spans) > 1 else None}
+        net._host_io[(B, H, W, str(dev))] = io
+    engines = io["engines"]
+    if engines[0].device != dev:
+        raise RuntimeError(f"net runs on {engines[0].device}, inference(device='{device}') requested")
+    key = ("nms_u8", float(prob_thresh), float(nms_iou_thresh))
+    io["hw"].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
+    results = [None] * B
+    trace = [] if _TRACE else None  # (label, seconds since entry): tools/diag_step.py prints it
+
+    def mark(label):
+        if trace is not None:
+            trace.append((label, time.perf_counter() - t_enter))
+
     with torch.cuda.device(dev):
-        io = eng.__dict__.setdefault("_host_io", {})
-        if not io:
-            io["img"] = _pinned((B, H, W, 3), torch.uint8)
-            io["hw"] = _pinned((B, 2), torch.int32)
-            io["meta"] = _pinned((2, B, C), torch.int32)
-            io["dst"] = _pinned((B, C), torch.int32)
-        stream = torch.cuda.current_stream()
-        _stack_into(io["img"].numpy(), images)  # raises ValueError on ragged shapes, like np.stack
-        io["hw"].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
-        eng.in_u8.copy_(io["img"], non_blocking=True)
-        eng.orig_hw.copy_(io["hw"], non_blocking=True)
-        eng.launch(("nms_u8", float(prob_thresh), float(nms_iou_thresh)))
-        io["meta"].copy_(eng.seg_meta, non_blocking=True)  # kept per (image, class) + first box per class
-        stream.synchronize()
-        meta = io["meta"].numpy()
-        dst_off, per_image = _destinations(meta[0], meta[1])
-        total = int(per_image.sum())
-        # results live in fresh pinned arrays (torch's caching host allocator recycles them once the
-        # caller drops the result), so the device writes the final dtypes and nothing is re-copied
-        if total == 0:
-            return [[np.zeros((0, 4), np.int64), np.zeros(0, np.float32), np.zeros(0, np.int64)] for _ in range(B)]
-        tlbr = _pinned((total, 4), torch.int64)
-        prob = _pinned((total,), torch.float32)
-        cls = _pinned((total,), torch.int64)
-        if True:
-            io["dst"].numpy()[...] = dst_off
-            eng.dst_off.copy_(io["dst"], non_blocking=True)
-            eng.emit()
-            tlbr.copy_(eng.out_tlbr[:total], non_blocking=True)
-            prob.copy_(eng.out_prob[:total], non_blocking=True)
-            cls.copy_(eng.out_cls[:total], non_blocking=True)
-            stream.synchronize()
-    tlbr, prob, cls = tlbr.numpy(), prob.numpy(), cls.numpy()
-    ends = np.cumsum(per_image).tolist()
-    results, pos = [], 0
-    for e in ends:
-        results.append([tlbr[pos:e], prob[pos:e], cls[pos:e]])
-        pos = e
+        caller = torch.cuda.current_stream()
+        streams = [st if st is not None else caller for st in io["streams"]]
+        img_np = io["img"].numpy()
+        # phase 1: stage + upload + launch, sub-batch after sub-batch
+        for (lo, hi), eng, st, meta in zip(spans, engines, streams, io["meta"]):
+            _stack_into(img_np[lo:hi], images[lo:hi])
+            mark(f"staged {lo}:{hi}")
+            if st is not caller:
+                st.wait_stream(caller)
+            with torch.cuda.stream(st):
+                eng.in_u8.copy_(io["img"][lo:hi], non_blocking=True)
+                eng.orig_hw.copy_(io["hw"][lo:hi], non_blocking=True)
+                eng.launch(key)
+                meta.copy_(eng.seg_meta, non_blocking=True)  # kept per (image, class) + first box per class
+            mark(f"launched {lo}:{hi}")
+        # phase 2: per sub-batch, as soon as its NMS is done: destinations -> emit -> download
+        base = 0
+        pending = []
+        for (lo, hi), eng, st, meta, dstbuf in zip(spans, engines, streams, io["meta"], io["dst"]):
+            st.synchronize()
+            mark(f"nms done {lo}:{hi}")
+            m = meta.numpy()
+            dst_off, per_image = _destinations(m[0], m[1])
+            total = int(per_image.sum())
+            eng.last_per_image = per_image
+            if total == 0:
+                for i in range(lo, hi):
+                    results[i] = [np.zeros((0, 4), np.int64), np.zeros(0, np.float32), np.zeros(0, np.int64)]
+                continue
+            # results live in fresh pinned arrays (torch's caching host allocator recycles them once
+            # the caller drops the result), so the device writes the final dtypes and nothing is re-copied
+            tlbr, prob, cls = _pinned((total, 4), torch.int64), _pinned((total,), torch.float32), _pinned((total,), torch.int64)
+            with torch.cuda.stream(st):
+                dstbuf.numpy()[...] = dst_off + base
+                eng.dst_off.copy_(dstbuf, non_blocking=True)
+                eng.emit(io["out"])
+                o = io["out"] if io["out"] is not None else (eng.out_tlbr, eng.out_prob, eng.out_cls)
+                tlbr.copy_(o[0][base:base + total], non_blocking=True)
+                prob.copy_(o[1][base:base + total], non_blocking=True)
+                cls.copy_(o[2][base:base + total], non_blocking=True)
+            pending.append((lo, st, tlbr, prob, cls, per_image))
+            base += total
+            mark(f"emit queued {lo}:{hi}")
+        io["last_total"], io["last_per_image"] = base, np.concatenate([e.last_per_image for e in engines])
+        for lo, st, tlbr, prob, cls, per_image in pending:
+            st.synchronize()
+            tlbr, prob, cls = tlbr.numpy(), prob.numpy(), cls.numpy()
+            pos = 0
+            for i, k in enumerate(per_image.tolist()):
+                results[lo + i] = [tlbr[pos:pos + k], prob[pos:pos + k], cls[pos:pos + k]]
+                pos += k
+        for st in streams:
+            if st is not caller:
+                caller.wait_stream(st)
+    mark("results built")
+    if trace is not None:
+        net._last_trace = trace
     return results
+
+
+def _sub_batches(batch):
+    """Contiguous spans ``inference`` pipelines through the GPU: 4 for batches of 32 and more, 2 from
+    16, otherwise the whole batch (``Y3_SUB_BATCHES`` overrides the count)."""
+    import os
+    n = int(os.environ.get("Y3_SUB_BATCHES", "0")) or (4 if batch >= 32 else 2 if batch >= 16 else 1)
+    n = max(1, min(n, batch))
+    base, rem = divmod(batch, n)
+    spans, lo = [], 0
+    for k in range(n):
+        hi = lo + base + (1 if k < rem else 0)
+        spans.append((lo, hi))
+        lo = hi
+    return spans
+
+
+def last_device_outputs(net, batch, height, width, device):
+    """Device-resident final arrays of the last ``inference`` call with this geometry:
+    ``(tlbr int64 [K,4], prob float32 [K], cls int64 [K], per_image int64 numpy [B])`` — what
+    ``distributed.gather_outputs`` sends between GPUs without a host round trip."""
+    io = net._host_io[(batch, height, width, str(_lib.require_device(device)))]
+    eng = io["engines"][0]
+    o = io["out"] if io["out"] is not None else (eng.out_tlbr, eng.out_prob, eng.out_cls)
+    k = io["last_total"]
+    return o[0][:k], o[1][:k], o[2][:k], io["last_per_image"]
 
 
 def non_max_suppression(bbox_tlbr, class_prob, class_idx=None, iou_thresh=0.3):

@@ -37,6 +37,20 @@ def _worker(rank, world, port, total_images, q):
         ok = len(got) == total_images
         for a, b in zip(got, everything):
             ok = ok and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
+        # device-to-device form (final arrays gathered on rank 0; CPU tensors under gloo)
+        import torch
+        mine = everything[lo:hi]
+        cat = [np.concatenate([m[j] for m in mine]) if mine else np.zeros((0, 4) if j == 0 else 0) for j in range(3)]
+        per_rank, cnts = D.gather_outputs(torch.from_numpy(cat[0].astype(np.int64).reshape(-1, 4)),
+                                          torch.from_numpy(cat[1].astype(np.float32)),
+                                          torch.from_numpy(cat[2].astype(np.int64)), [len(m[1]) for m in mine])
+        ok = ok and cnts.tolist() == [len(e[1]) for e in everything]
+        if rank == 0:
+            for j in range(3):
+                whole = np.concatenate([pr[j].numpy() for pr in per_rank])
+                ok = ok and np.array_equal(whole, np.concatenate([e[j] for e in everything]))
+        else:
+            ok = ok and per_rank is None
         q.put((rank, bool(ok), lo, hi))
     finally:
         dist.destroy_process_group()

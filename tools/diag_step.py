@@ -48,6 +48,10 @@ def main():
         yolov3_b200.inference(net, lists, device="cuda:0", prob_thresh=bench.PROB_THRESH,
                               nms_iou_thresh=bench.IOU_THRESH, resize=False)
     print("inference(): %.2f ms per 64-image call" % ((time.perf_counter() - t0) / 5 * 1e3))
+    if getattr(net, "_last_trace", None):  # Y3_TRACE=1: host timeline of the last call
+        print("host timeline of the last call (ms since entry):")
+        for label, t in net._last_trace:
+            print(f"  {t * 1e3:7.3f}  {label}")
     pr = cProfile.Profile()
     pr.enable()
     for _ in range(5):
