@@ -231,7 +231,7 @@ def main_ours(args, rank, local_rank, world):
 
     # ---- e2e through the public API, host buffers ------------------------------------------------
     host_lists = [list(b) for b in host_batches]
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 40))
     for i in range(5):  # every one of the four rotating batches once: pinned result buffers reach steady state
         yolov3_b200.inference(net, host_lists[i % 4], device=str(dev), prob_thresh=PROB_THRESH,
                               nms_iou_thresh=IOU_THRESH, resize=False)

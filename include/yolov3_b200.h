@@ -103,9 +103,9 @@ int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w,
  *  y3_conv_chain_stem_u8: uint8 BGR HWC images [N,H,W,3] -> RGB /255 (yolov3/inference.py:332-333)
  *    -> conv 3x3 / stride 1 / pad 1, 3 -> 32 (+BN folded, leaky)  -> conv 3x3 / stride 2 / pad 1,
  *    32 -> 64 (+BN folded, leaky): blocks 0 and 1 of models/yolov3.cfg / yolov3-spp.cfg
- *    (built at yolov3/darknet.py:244-257).  w1: bf16 [32][32] = the 27 taps in (r,s,rgb) order
- *    padded to 32; w2: bf16 [64][3][3][32].  y: NHWC bf16 [N,H/2,W/2,64] pitch ld_y.
- *    H/2 must be a multiple of 16 and W/2 a multiple of 8.
+ *    (built at yolov3/darknet.py:244-257).  w1: bf16 [32][3][16] = per filter row r the 9 taps in
+ *    (s, BGR byte) order — the image's own byte order — padded to 16; w2: bf16 [64][3][3][32].  y: NHWC bf16 [N,H/2,W/2,64] pitch ld_y.
+ *    H/2 must be a multiple of 16 and W/2 a multiple of 8; img 8-byte aligned.
  *
  *  y3_conv_chain_res64: one residual unit x -> conv 1x1 64 -> 32 -> conv 3x3 / 1 / pad 1 32 -> 64,
  *    + x (the [shortcut] of yolov3/darknet.py:376-379).  x: NHWC bf16 [N,H,W,64] pitch ld_x;

@@ -10,8 +10,9 @@
 //         (one Darknet residual unit incl. its [shortcut], darknet.py:376-379)
 //
 // Per CTA: TEAMS independent teams of 4 warps, each looping over 8(w) x 16(h) output tiles:
-//   stage 1  A = im2col rows built by the team from the image patch (STEM) or the x patch with
-//            halo fetched by one 4-D TMA (RES);  D1[pixel of the patch][32] in TMEM
+//   stage 1  STEM: one 32-byte A row per image-patch pixel (its BGR bytes and its two right neighbours'),
+//            the three filter rows = three MMAs over the same rows shifted by one patch row each;
+//            RES: the x patch with halo fetched by one 4-D TMA.  D1[pixel of the patch][32] in TMEM
 //   epi 1    tcgen05.ld -> +bias, leaky, ZERO outside the image (stage 2's padding) -> bf16
 //            patch in smem, laid out (swizzled) exactly as a K-major UMMA operand
 //   stage 2  nine taps = nine descriptor START OFFSETS into that one patch (row stride of the
@@ -40,30 +41,35 @@ struct ChainCfg {
   static constexpr int TW = 8, TH = 16;             // stage-2 output tile (M = 128 rows = 16 groups of 8)
   static constexpr int S2 = STEM ? 2 : 1;           // stage-2 stride
   static constexpr int CM = 32, C2 = 64;            // intermediate / output channels
-  static constexpr int K1 = STEM ? 32 : 64;         // stage-1 K (27 taps padded to 32 | 64 channels)
   static constexpr int PH = (TH - 1) * S2 + 3;      // patch rows of the intermediate: 33 | 18
   static constexpr int PWM = STEM ? 18 : 10;        // patch pitch in pixels (even for pixel pairs)
   static constexpr int NP = PH * PWM;               // 594 | 180 patch pixels = stage-1 GEMM rows
   static constexpr int MT1 = (NP + 127) / 128;      // 5 | 2 stage-1 M tiles
-  static constexpr int A1_SPAN = K1 * 2;            // bytes per stage-1 A row: 64 | 128
-  static constexpr int W1_BYTES = CM * A1_SPAN;     // 2048 | 4096
+  // Stage-1 A rows.  STEM: one 32-byte row per pixel of the (PH + 2) x PWM input patch = the 3 x BGR
+  // bytes of that pixel and its two right neighbours (9 values, K padded to 16); the three filter
+  // rows dy are three MMAs whose A operand starts dy * PWM rows further down.  RES: 128-byte rows of x.
+  static constexpr int A1_SPAN = STEM ? 32 : 128;
+  static constexpr int K1_STEPS = STEM ? 3 : 4;     // K = 16 MMAs per stage-1 M tile
+  static constexpr int W1_BYTES = CM * A1_SPAN * (STEM ? 3 : 1);  // 3072 | 4096
   static constexpr int W2_TAP_BYTES = C2 * CM * 2;  // 4096
   static constexpr int W2_BYTES = 9 * W2_TAP_BYTES;
   static constexpr int BIAS_BYTES = (CM + C2) * 4;  // both bias vectors, read as broadcast LDS.128
   // Team-private regions.  Swizzles are functions of the absolute smem address, so operands only need
-  // 128-byte alignment: STEM's intermediate patch overlays the (dead) im2col rows; RES's two x-patch
+  // 128-byte alignment: STEM's intermediate patch overlays the (dead) stage-1 rows; RES's two x-patch
   // buffers are packed back to back and the output slab overlays the (dead) intermediate.
-  static constexpr int A1_BYTES = STEM ? MT1 * 128 * A1_SPAN : NP * A1_SPAN;  // 40960 | 23040
+  static constexpr int IMG_ROWS = PH + 2, IMG_PITCH = 64;           // STEM image patch: 35 rows x 64 bytes
+  static constexpr int A1_ROWS = STEM ? (MT1 * 128 + 2 * PWM + 4) : NP;  // incl. the last M tile's over-read
+  static constexpr int A1_BYTES = STEM ? round_up_c(round_up_c(A1_ROWS * A1_SPAN, 1024), 1024) : NP * A1_SPAN;
   static constexpr int A1_BUFS = STEM ? 1 : 2;      // RES: x patch of the next tile is prefetched
+  static constexpr int MID_BYTES = round_up_c(NP * CM * 2, 1024);   // 38912 | 12288
   static constexpr int STG_BYTES = 128 * C2 * 2;    // 16384
-  static constexpr int IMG_ROWS = PH + 2, IMG_PITCH = 60;           // STEM image patch: 35 rows x 20 px x 3
   static constexpr int IMG_BYTES = STEM ? round_up_c(IMG_ROWS * IMG_PITCH * 2, 1024) : 0;
   static constexpr int OFF_MID = STEM ? 0 : A1_BUFS * A1_BYTES;     // 0 | 46080
-  static constexpr int OFF_STG = STEM ? A1_BYTES : OFF_MID;         // 40960 | 46080
+  static constexpr int OFF_STG = STEM ? (A1_BYTES > MID_BYTES ? A1_BYTES : MID_BYTES) : OFF_MID;  // 38912 | 46080
   static constexpr int OFF_IMG = OFF_STG + STG_BYTES;
-  static constexpr int TEAM_BYTES = OFF_IMG + IMG_BYTES;            // 62464 | 62464
+  static constexpr int TEAM_BYTES = OFF_IMG + IMG_BYTES;            // 60416 | 62464
   static_assert(TEAM_BYTES % 1024 == 0 && OFF_STG % 1024 == 0 && OFF_MID % 1024 == 0, "region alignment");
-  static_assert(NP * CM * 2 <= (STEM ? A1_BYTES : STG_BYTES), "intermediate patch must fit its overlay");
+  static_assert(STEM || NP * CM * 2 <= STG_BYTES, "intermediate patch must fit its overlay");
   // the stage-2 accumulator overlays the stage-1 accumulators (drained by epilogue 1 before stage 2 starts)
   static constexpr int TMEM_COLS_TEAM = MT1 * CM;   // 160 | 64
   static constexpr int TMEM_COLS = TEAMS * TMEM_COLS_TEAM <= 256 ? 256 : 512;
@@ -72,8 +78,8 @@ struct ChainCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // stage-1 over-read of the last M tile (rows NP..MT1*128) must stay inside the team region
   static_assert(STEM || ((A1_BUFS - 1) * A1_BYTES + MT1 * 128 * A1_SPAN <= TEAM_BYTES), "RES stage-1 over-read");
-  static constexpr int IMG_U16 = IMG_ROWS * (IMG_PITCH / 2);  // 1050 two-byte loads per image patch
-  static constexpr int IMG_PRE = (IMG_U16 + TEAM_THREADS - 1) / TEAM_THREADS;  // 9 per thread
+  static constexpr int IMG_WORDS = IMG_ROWS * (IMG_PITCH / 4);  // 560 four-byte loads per image patch
+  static constexpr int IMG_PRE = (IMG_WORDS + TEAM_THREADS - 1) / TEAM_THREADS;  // 5 per thread
 };
 
 struct ChainParams {
@@ -96,6 +102,26 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
   return r;
 }
+// packed fp32 pairs (FADD2 / FMUL2): same IEEE results as the scalar forms, half the issue slots
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return r;
+}
+// leaky(v) = max(v, slope * v) for slope <= 1 (slope 1 = identity)
+__device__ __forceinline__ float2 leaky2(float2 v, float2 slope) {
+  const float2 t = fmul2(v, slope);
+  return make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
+}
+__device__ __forceinline__ uint32_t swz32(uint32_t a) { return a ^ (((a >> 7) & 1u) << 4); }
+
 // K-major smem descriptor: start address, SBO (bytes between 8-row groups), layout 2/4/6 = SW128/64/32
 __device__ __forceinline__ uint64_t chain_desc(uint32_t addr, uint32_t sbo_bytes, uint64_t layout) {
   return (uint64_t(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61) | (1ull << 16) | uint64_t((addr >> 4) & 0x3FFFu);
@@ -162,7 +188,11 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   if (threadIdx.x == 0) {  // resident weights of both layers
     ptx::mbar_arrive_expect_tx(wbar, Cfg::W1_BYTES + Cfg::W2_BYTES);
-    ptx::tma_load_2d(w1_s, &tmap_w1, wbar, 0, 0);
+    if constexpr (STEM) {
+      for (int dy = 0; dy < 3; ++dy) ptx::tma_load_2d(w1_s + dy * Cfg::CM * Cfg::A1_SPAN, &tmap_w1, wbar, dy * 16, 0);
+    } else {
+      ptx::tma_load_2d(w1_s, &tmap_w1, wbar, 0, 0);
+    }
     for (int tap = 0; tap < 9; ++tap) ptx::tma_load_2d(w2_s + tap * Cfg::W2_TAP_BYTES, &tmap_w2, wbar, tap * Cfg::CM, 0);
   }
 
@@ -170,8 +200,11 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int team_step = gridDim.x * Cfg::TEAMS;
   const uint32_t bar_id = 1 + team;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const float slope1 = p.leaky1 ? 0.1f : 1.0f;  // leaky(v) = max(v, 0.1 v); identity = max(v, v)
-  const float slope2 = p.leaky2 ? 0.1f : 1.0f;
+  const float2 slope1 = p.leaky1 ? make_float2(0.1f, 0.1f) : make_float2(1.f, 1.f);  // leaky(v) = max(v, 0.1 v)
+  const float2 slope2 = p.leaky2 ? make_float2(0.1f, 0.1f) : make_float2(1.f, 1.f);
+  float2 bias1[Cfg::CM / 2];  // every thread applies all 32 stage-1 biases to its patch pixel
+#pragma unroll
+  for (int q = 0; q < Cfg::CM / 2; ++q) bias1[q] = __ldg(reinterpret_cast<const float2*>(p.bias1) + q);
   auto tile_origin = [&](int tile, int& b, int& y0, int& x0) {
     b = tile / tiles_per_img;
     const int rem = tile - b * tiles_per_img;
@@ -180,44 +213,25 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     x0 = (rem - ty * p.tiles_x) * Cfg::TW;
   };
 
-  // ---- STEM: register prefetch of the next tile's uint8 patch (two bytes per load).  Element e of the
-  // patch (row r = e/30, byte pair c = e%30) belongs to this thread for e = i*128 + tid; (r, c) and the
-  // bf16 destinations of its two bytes do not depend on the tile and are computed once.
+  // ---- STEM: register prefetch of the next tile's uint8 patch: 35 rows x 64 bytes starting one BGR
+  // pixel + 2 bytes left of the tile's first needed pixel, which makes every row 8-byte aligned.
+  // Word e = i * 128 + tid of the patch is row e / 16, byte 4 (e % 16).
   uint32_t pre[STEM ? Cfg::IMG_PRE : 1];
-  uint32_t pre_rc[STEM ? Cfg::IMG_PRE : 1];   // r | c << 8 | valid << 16
-  uint32_t pre_dst[STEM ? Cfg::IMG_PRE : 1];  // patch index of byte 0 | of byte 1 << 16
-  if constexpr (STEM) {
-#pragma unroll
-    for (int i = 0; i < Cfg::IMG_PRE; ++i) {
-      const int e = i * Cfg::TEAM_THREADS + tid;
-      const int r = e / (Cfg::IMG_PITCH / 2);
-      const int c = e - r * (Cfg::IMG_PITCH / 2);
-      pre_rc[i] = uint32_t(r) | (uint32_t(c) << 8) | (e < Cfg::IMG_U16 ? 1u << 16 : 0u);
-      uint32_t d[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = 2 * c + h;  // byte column: pixel j/3, BGR byte j%3 -> RGB channel 2 - j%3
-        const int px = j / 3;
-        d[h] = uint32_t(r * Cfg::IMG_PITCH + px * 3 + (2 - (j - px * 3)));
-      }
-      pre_dst[i] = d[0] | (d[1] << 16);
-      pre[i] = 0;
-    }
-  }
   auto img_prefetch = [&](int tile) {
     if constexpr (STEM) {
       int b, y0, x0;
       tile_origin(tile, b, y0, x0);
-      const int byte0 = 6 * x0 - 6;  // first byte of the patch row inside the image row (even)
+      const int byte0 = 6 * x0 - 8;
       const int row_bytes = 3 * p.Wm;
       const uint8_t* const base = p.img + (long long)b * p.Hm * row_bytes;
 #pragma unroll
       for (int i = 0; i < Cfg::IMG_PRE; ++i) {
-        const int iy = 2 * y0 - 2 + int(pre_rc[i] & 0xffu);
-        const int byte = byte0 + 2 * int((pre_rc[i] >> 8) & 0xffu);
-        const bool ok = (pre_rc[i] >> 16) != 0 && iy >= 0 && iy < p.Hm && byte >= 0 && byte < row_bytes;
+        const int e = i * Cfg::TEAM_THREADS + tid;
+        const int iy = 2 * y0 - 2 + (e >> 4);
+        const int byte = byte0 + 4 * (e & 15);
+        const bool ok = e < Cfg::IMG_WORDS && iy >= 0 && iy < p.Hm && byte >= 0 && byte < row_bytes;
         uint32_t v = 0;
-        if (ok) v = __ldg(reinterpret_cast<const unsigned short*>(base + (long long)iy * row_bytes + byte));
+        if (ok) v = __ldg(reinterpret_cast<const unsigned int*>(base + (long long)iy * row_bytes + byte));
         pre[i] = v;
       }
     }
@@ -245,39 +259,35 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t a1_s = team_s + cur * Cfg::A1_BYTES;
 
     if constexpr (STEM) {
-      // (1) image bytes -> bf16 RGB/255 patch [35][20 px][3]  (inference.py:332-333).  v * fl(1/255)
-      // rounds to the same bf16 as the reference's fp32 v / 255 for all 256 byte values.
-      __nv_bfloat16* const patch = reinterpret_cast<__nv_bfloat16*>(smem_gen + (team_s + Cfg::OFF_IMG - smem_base));
+      // (1) image bytes -> bf16 /255 patch [35][64], still in BGR byte order (the first layer's weights are
+      // laid out to match).  v * fl(1/255) rounds to the same bf16 as the reference's fp32 v / 255 for
+      // all 256 byte values (inference.py:332-333).
+      const uint32_t patch_s = team_s + Cfg::OFF_IMG;
 #pragma unroll
       for (int i = 0; i < Cfg::IMG_PRE; ++i) {
-        if (pre_rc[i] >> 16) {
-          const float v0 = __fmul_rn((float)(pre[i] & 0xffu), 0.003921568859368563f);
-          const float v1 = __fmul_rn((float)((pre[i] >> 8) & 0xffu), 0.003921568859368563f);
-          patch[pre_dst[i] & 0xffffu] = __float2bfloat16_rn(v0);
-          patch[pre_dst[i] >> 16] = __float2bfloat16_rn(v1);
+        const int e = i * Cfg::TEAM_THREADS + tid;
+        if (e < Cfg::IMG_WORDS) {
+          const float k = 0.003921568859368563f;
+          const uint32_t lo = pack_bf16x2(__fmul_rn((float)(pre[i] & 0xffu), k), __fmul_rn((float)((pre[i] >> 8) & 0xffu), k));
+          const uint32_t hi = pack_bf16x2(__fmul_rn((float)((pre[i] >> 16) & 0xffu), k), __fmul_rn((float)(pre[i] >> 24), k));
+          asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(patch_s + 8 * e), "r"(lo), "r"(hi) : "memory");
         }
       }
       ptx::named_bar_sync(bar_id, Cfg::TEAM_THREADS);
       if (tile + team_step < p.num_tiles) img_prefetch(tile + team_step);
-      // (2) im2col rows of the first layer: row = patch pixel, K = (dy, dx, rgb) 27 -> 32
-      const unsigned short* const pu = reinterpret_cast<const unsigned short*>(patch);
-      for (int pi = tid; pi < Cfg::NP; pi += Cfg::TEAM_THREADS) {
-        const int mr = pi / Cfg::PWM;
-        const int mc = pi - mr * Cfg::PWM;
-        const unsigned short* src = pu + mr * Cfg::IMG_PITCH + mc * 3;
-        uint32_t v[28];
+      // (2) stage-1 A rows: row q = r * 18 + c holds the 9 values of patch pixels c, c+1, c+2 of row r
+      // (pixel c starts at value 2 + 3c), K padded to 16
+      const unsigned short* const pu = reinterpret_cast<const unsigned short*>(smem_gen + (patch_s - smem_base));
+      for (int q = tid; q < Cfg::IMG_ROWS * Cfg::PWM; q += Cfg::TEAM_THREADS) {
+        const int r = q / Cfg::PWM;
+        const int c = q - r * Cfg::PWM;
+        const unsigned short* src = pu + r * Cfg::IMG_PITCH + 2 + 3 * c;
+        uint32_t v[9];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int j = 0; j < 9; ++j) v[dy * 9 + j] = src[dy * Cfg::IMG_PITCH + j];
-        v[27] = 0;
-        uint32_t w[16];
-#pragma unroll
-        for (int q = 0; q < 14; ++q) w[q] = v[2 * q] | (v[2 * q + 1] << 16);
-        w[14] = 0; w[15] = 0;
-        const uint32_t row = a1_s + pi * Cfg::A1_SPAN;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sts128(swz64(row + c * 16), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        for (int j = 0; j < 9; ++j) v[j] = src[j];
+        const uint32_t row = a1_s + q * Cfg::A1_SPAN;
+        sts128(swz32(row), v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        sts128(swz32(row + 16), v[8], 0u, 0u, 0u);
       }
       ptx::fence_proxy_async();
     } else {
@@ -299,14 +309,26 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ---- stage 1 MMAs ----
     if (tid == 0) {
       ptx::tc_fence_after();
-      constexpr uint64_t L1 = STEM ? 4 : 2;  // SW64 | SW128
-      const uint64_t db = chain_desc(w1_s, 8 * Cfg::A1_SPAN, L1);
+      if constexpr (STEM) {
+        // filter row dy: same A rows shifted by dy * PWM (next patch row), weights slice dy; SW32 rows
 #pragma unroll
-      for (int t = 0; t < Cfg::MT1; ++t) {
-        const uint64_t da = chain_desc(a1_s + t * 128 * Cfg::A1_SPAN, 8 * Cfg::A1_SPAN, L1);
+        for (int t = 0; t < Cfg::MT1; ++t) {
 #pragma unroll
-        for (int k = 0; k < Cfg::K1 / 16; ++k)
-          ptx::umma_bf16_ss<1>(tmem_team + t * Cfg::CM, da + 2u * k, db + 2u * k, chain_idesc(Cfg::CM), k != 0);
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t da = chain_desc(a1_s + (t * 128 + dy * Cfg::PWM) * Cfg::A1_SPAN, 8 * Cfg::A1_SPAN, 6);
+            const uint64_t db = chain_desc(w1_s + dy * Cfg::CM * Cfg::A1_SPAN, 8 * Cfg::A1_SPAN, 6);
+            ptx::umma_bf16_ss<1>(tmem_team + t * Cfg::CM, da, db, chain_idesc(Cfg::CM), dy != 0);
+          }
+        }
+      } else {
+        const uint64_t db = chain_desc(w1_s, 8 * Cfg::A1_SPAN, 2);
+#pragma unroll
+        for (int t = 0; t < Cfg::MT1; ++t) {
+          const uint64_t da = chain_desc(a1_s + t * 128 * Cfg::A1_SPAN, 8 * Cfg::A1_SPAN, 2);
+#pragma unroll
+          for (int k = 0; k < Cfg::K1_STEPS; ++k)
+            ptx::umma_bf16_ss<1>(tmem_team + t * Cfg::CM, da + 2u * k, db + 2u * k, chain_idesc(Cfg::CM), k != 0);
+        }
       }
       ptx::umma_commit<1>(mma_bar);
     }
@@ -330,22 +352,21 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int mx = x0 * Cfg::S2 - 1 + mc;
         const bool inside = my >= 0 && my < p.Hm && mx >= 0 && mx < p.Wm;
         const uint32_t row = mid_s + pi * (Cfg::CM * 2);
+        uint32_t w[16];
+        if (inside) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 a = leaky2(fadd2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), bias1[q]), slope1);
+            w[q] = pack_bf16x2(a.x, a.y);
+          }
+        } else {  // stage 2's zero padding applies to the intermediate, not to stage 1's input
+#pragma unroll
+          for (int q = 0; q < 16; ++q) w[q] = 0u;
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 ba = lds128(bias_s + c * 32), bb = lds128(bias_s + c * 32 + 16);
-          const float bq[8] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w),
-                               __uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
-          uint32_t w[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float a = __uint_as_float(v[8 * c + 2 * q]) + bq[2 * q];
-            float d = __uint_as_float(v[8 * c + 2 * q + 1]) + bq[2 * q + 1];
-            a = fmaxf(a, slope1 * a);
-            d = fmaxf(d, slope1 * d);
-            w[q] = inside ? pack_bf16x2(a, d) : 0u;
-          }
           const uint32_t a = STEM ? swz128(row + c * 16) : swz64(row + c * 16);
-          sts128(a, w[0], w[1], w[2], w[3]);
+          sts128(a, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         }
       }
     }
@@ -383,32 +404,28 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         uint32_t v[16];
         ptx::tmem_ld_x16(tmem_team + tlane + cc * 16, v);
         ptx::tmem_ld_wait();
-        float f[16];
+        float2 f[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 bq = lds128(bias_s + Cfg::CM * 4 + cc * 64 + q * 16);
-          f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + __uint_as_float(bq.x);
-          f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + __uint_as_float(bq.y);
-          f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(bq.z);
-          f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(bq.w);
+          f[2 * q] = fadd2(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])),
+                           make_float2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+          f[2 * q + 1] = fadd2(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])),
+                               make_float2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], slope2 * f[j]);
+        for (int j = 0; j < 8; ++j) f[j] = leaky2(f[j], slope2);
         if constexpr (!STEM) {
           const uint4 r0 = lds128(swz128(rrow + (2 * cc) * 16));
           const uint4 r1 = lds128(swz128(rrow + (2 * cc + 1) * 16));
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 t2 = unpack_bf16x2(rr[j]);
-            f[2 * j] += t2.x;
-            f[2 * j + 1] += t2.y;
-          }
+          for (int j = 0; j < 8; ++j) f[j] = fadd2(f[j], unpack_bf16x2(rr[j]));
         }
-        sts128(swz128(srow + (2 * cc) * 16), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-               pack_bf16x2(f[6], f[7]));
-        sts128(swz128(srow + (2 * cc + 1) * 16), pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-               pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+        sts128(swz128(srow + (2 * cc) * 16), pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
+               pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
+        sts128(swz128(srow + (2 * cc + 1) * 16), pack_bf16x2(f[4].x, f[4].y), pack_bf16x2(f[5].x, f[5].y),
+               pack_bf16x2(f[6].x, f[6].y), pack_bf16x2(f[7].x, f[7].y));
       }
     }
     ptx::tc_fence_before();
@@ -439,7 +456,7 @@ static int launch_chain(const y3_chain_desc* d, const void* x, const void* w1, c
   const int w2o = STEM ? (d->w - 1) / 2 + 1 : d->w;
   Y3_CHECK_ARG(h2 % Cfg::TH == 0 && w2o % Cfg::TW == 0,
                "conv chain: output %dx%d must tile by %dx%d", h2, w2o, Cfg::TH, Cfg::TW);
-  Y3_CHECK_ARG(!STEM || (d->w % 2 == 0 && d->h % 2 == 0), "conv chain stem: image sides must be even");
+  Y3_CHECK_ARG(!STEM || (d->w % 8 == 0 && d->h % 2 == 0), "conv chain stem: image width must be a multiple of 8");
 
   ChainParams p;
   p.B = d->n; p.H2 = h2; p.W2 = w2o;
@@ -455,10 +472,11 @@ static int launch_chain(const y3_chain_desc* d, const void* x, const void* w1, c
   alignas(64) CUtensorMap tx, tw1, tw2, ty;
   memset(&tx, 0, sizeof(tx));
   int rc;
-  {
-    const uint64_t dims[2] = {(uint64_t)Cfg::K1, (uint64_t)Cfg::CM};
-    const uint64_t str[1] = {(uint64_t)Cfg::A1_SPAN};
-    const uint32_t box[2] = {(uint32_t)Cfg::K1, (uint32_t)Cfg::CM};
+  {  // stage-1 weights: STEM [32][3 dy][16] read as three [16 x 32] boxes; RES [32][64]
+    const uint64_t kk = STEM ? 48 : 64;
+    const uint64_t dims[2] = {kk, (uint64_t)Cfg::CM};
+    const uint64_t str[1] = {kk * 2};
+    const uint32_t box[2] = {(uint32_t)(STEM ? 16 : 64), (uint32_t)Cfg::CM};
     if ((rc = encode_tiled_map(&tw1, 2, w1, dims, str, box, Cfg::A1_SPAN)) != Y3_OK) return rc;
   }
   {
@@ -476,9 +494,9 @@ static int launch_chain(const y3_chain_desc* d, const void* x, const void* w1, c
   }
   if (!STEM) {
     const uint64_t pix = (uint64_t)d->ld_x * 2;
-    const uint64_t dims[4] = {(uint64_t)Cfg::K1, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    const uint64_t dims[4] = {64, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     const uint64_t str[3] = {pix, pix * d->w, pix * d->w * d->h};
-    const uint32_t box[4] = {(uint32_t)Cfg::K1, (uint32_t)Cfg::PWM, (uint32_t)Cfg::PH, 1};
+    const uint32_t box[4] = {64, (uint32_t)Cfg::PWM, (uint32_t)Cfg::PH, 1};
     if ((rc = encode_tiled_map(&tx, 4, x, dims, str, box, 128)) != Y3_OK) return rc;
   }
 
@@ -509,7 +527,7 @@ int y3_conv_chain_stem_u8(const y3_chain_desc* d, const uint8_t* img, const void
   Y3_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "conv chain stem: bad shape");
   Y3_CHECK_ARG(d->ld_y >= 64 && d->ld_y % 8 == 0, "conv chain stem: ld_y=%d invalid", d->ld_y);
   Y3_CHECK_ARG(aligned16(w1) && aligned16(w2) && aligned16(y) && aligned16(b1) && aligned16(b2) &&
-               (reinterpret_cast<uintptr_t>(img) & 1) == 0, "conv chain stem: alignment");
+               (reinterpret_cast<uintptr_t>(img) & 7) == 0, "conv chain stem: alignment");
   return launch_chain<CHAIN_STEM>(d, img, w1, b1, w2, b2, y, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -320,7 +320,7 @@ class Engine:
                     self.stem = sfn
                     self.conv_ops.insert(0, (0, sfn, sum(f for _, _, f in self.conv_ops_unfused_stem)))
                 elif in_stem:
-                    self._stem_w0 = (w, bias)
+                    self._stem_w0 = self._stem_first_weights(bias)
                 if head:
                     heads.append((i + 1, yv))
             elif t == "maxpool":
@@ -472,6 +472,25 @@ class Engine:
             del cache[k_]
         cache[key] = out
         return out
+
+    def _stem_first_weights(self, bias):
+        """Block 0 (3x3 over RGB) for the fused uint8 stem: bf16 ``[32][3 filter rows][16]`` with the
+        9 taps of a filter row in (column, BGR byte) order — the image's byte order — padded to 16."""
+        cache = self.net.__dict__.setdefault("_folded_cache", {})
+        key = (self.net._weights_version, "stem0", str(self.device))
+        if key not in cache:
+            seq = self.net.modules_[0]
+            with torch.no_grad():
+                W = seq[0].weight.detach().to(self.device, torch.float32)  # [32, rgb, dy, dx]
+                if len(seq) > 1 and isinstance(seq[1], torch.nn.BatchNorm2d):
+                    bn = seq[1]
+                    W = W * (bn.weight.detach().to(self.device, torch.float32) / torch.sqrt(
+                        bn.running_var.detach().to(self.device, torch.float32) + bn.eps)).view(-1, 1, 1, 1)
+                Wk = torch.zeros(W.shape[0], 3, 16, device=self.device, dtype=torch.float32)
+                # [n, dy, dx, byte] with byte b = BGR position -> channel 2 - b
+                Wk[:, :, :9] = W.flip(1).permute(0, 2, 3, 1).reshape(W.shape[0], 3, 9)
+                cache[key] = Wk.to(torch.bfloat16).contiguous()
+        return cache[key], bias
 
     # ------------------------------------------------------------------------------------
     # execution

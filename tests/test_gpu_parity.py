@@ -325,12 +325,13 @@ def test_micro_network_teacher_forced_convs(micro):
 
 def oracle_tail_from_engine_logits(net, eng, orig_shapes, prob_thresh, iou, imgs=None):
     """Decode + post-process + NMS on the CPU oracle from the engine's OWN head logits.  Heads that
-    decode inside the convolution epilogue never write their logits: pass the images and the
-    float-input program (same kernels, same accumulators — test_uint8_stem_program_equals_float_program)
-    is run on the same pixels to materialise them."""
+    decode inside the convolution epilogue never write their logits: pass the images and the same
+    uint8 program is re-run with the logits-writing form of the head convolutions (identical
+    accumulators) to materialise them."""
     if eng.num_fused_heads:
         assert imgs is not None
-        net.forward(torch.from_numpy(PO.preprocess(list(imgs))).to(dev()))
+        eng.in_u8.copy_(torch.from_numpy(np.stack(imgs)).to(dev()))
+        eng.run_backbone(fused_stem=True, fused_heads=False)  # same launches, heads write their logits
         torch.cuda.synchronize()
     boxes, probs, idxs = [], [], []
     yolo_blocks = [b for b in net.blocks if b["type"] == "yolo"]
@@ -578,8 +579,9 @@ def _rand_conv(g, cout, cin, k):
 
 @pytest.mark.parametrize("n,H,W", [(1, 32, 32), (2, 64, 96), (3, 416, 416)])
 def test_conv_chain_stem_equals_unfused_launches_and_oracle(n, H, W):
-    """uint8 image -> conv0 -> conv1 in one kernel: bit-identical to im2col + two y3_conv2d launches
-    (same bf16 intermediate, same accumulation order) and within the conv bar of the fp32 oracle."""
+    """uint8 image -> conv0 -> conv1 in one kernel vs im2col + two y3_conv2d launches (same bf16
+    intermediate; the first layer's taps are grouped per filter row, so its fp32 accumulation order
+    differs: results agree to bf16 rounding) and within the conv bar of the fp32 oracle."""
     g = torch.Generator().manual_seed(31)
     u = torch.randint(0, 256, (n, H, W, 3), generator=g, dtype=torch.uint8)
     p0, p1 = _rand_conv(g, 32, 3, 3), _rand_conv(g, 64, 32, 3)
@@ -589,8 +591,12 @@ def test_conv_chain_stem_equals_unfused_launches_and_oracle(n, H, W):
     b0 = p0["bias"].to(dev()).contiguous()
     w1, b1 = fold(p1, 32, 64)
     ud = u.to(dev())
+    # stem layout of the first layer: [32][dy][dx * 3 + BGR byte], 9 -> 16
+    w0s = torch.zeros(32, 3, 16)
+    w0s[:, :, :9] = p0["weight"].flip(1).permute(0, 2, 3, 1).reshape(32, 3, 9)
+    w0s = w0s.to(dev(), torch.bfloat16).contiguous()
     y = torch.full((n, H // 2, W // 2, 64), 7.0, device=dev(), dtype=torch.bfloat16)
-    _lib.conv_chain_stem_u8(ud, w0, b0, w1, b1, y.data_ptr(), ld_y=64)
+    _lib.conv_chain_stem_u8(ud, w0s, b0, w1, b1, y.data_ptr(), ld_y=64)
     # unfused launches
     col = torch.empty(n, H, W, 32, device=dev(), dtype=torch.bfloat16)
     _lib.im2col3x3_bgr_u8(ud, col, 32)
@@ -601,7 +607,9 @@ def test_conv_chain_stem_equals_unfused_launches_and_oracle(n, H, W):
     _lib.conv2d(a0.data_ptr(), w1, b1, a1.data_ptr(), n=n, h=H, w_in=W, cin=32, cout=64, ksize=3, stride=2, pad=1,
                 ld_x=32, ld_y=64, leaky=True)
     torch.cuda.synchronize()
-    assert torch.equal(y, a1), float((y.float() - a1.float()).abs().max())
+    diff = (y.float() - a1.float()).abs()
+    assert float(diff.max()) <= 2.0 ** -6 * float(a1.float().abs().max())  # a couple of bf16 ulps at most
+    assert float((diff > 0).float().mean()) < 0.02
     if H <= 96:  # fp32 oracle on the reference's own preprocessing
         xf = torch.from_numpy(PO.preprocess(list(u.numpy())))
         mid = F.leaky_relu(F.conv2d(xf.bfloat16().float(), p0["weight"].bfloat16().float(), p0["bias"], padding=1), 0.1)
@@ -655,7 +663,7 @@ def test_conv_chain_rejects_bad_arguments():
 
 def test_uint8_stem_program_equals_float_program(yolov3_full):
     """inference()'s program (fused uint8 stem) and Darknet.forward's (packed float input, blocks 0-1
-    as separate launches) must produce identical head logits for the same pixels."""
+    as separate launches) see the same pixels: head logits agree to bf16-rounding noise."""
     net, *_ = yolov3_full
     rng = np.random.default_rng(3)
     imgs = rng.integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
@@ -671,7 +679,11 @@ def test_uint8_stem_program_equals_float_program(yolov3_full):
     eng.run_backbone(fused_stem=True, fused_heads=False)
     torch.cuda.synchronize()
     for (_, logits), w in zip(eng.head_descs, want):
-        assert torch.equal(logits, w)
+        # same kernels except blocks 0-1 (fused stem: different fp32 accumulation grouping in block 0)
+        # (random-weight YOLOv3 amplifies a 1-ulp bf16 perturbation 40-90x end to end)
+        mx, mean = float((logits - w).abs().max()), float((logits - w).abs().mean())
+        print(f"uint8 vs float program logits: max|d| {mx:.4f}, mean|d| {mean:.5f}, max|ref| {float(w.abs().max()):.2f}")
+        assert mean <= 2e-2 * float(w.abs().max())
 
 
 def test_fused_head_decode_equals_standalone_decode(yolov3_full):
