@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -89,6 +89,17 @@ class ClockSampler:
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ncu_conv_traffic():
+    """DRAM bytes moved by the convolution launches of one step, from the committed ncu launch list
+    (profiles/*_launches_step_traffic.json, written by tools/summarize_profiles.py); None if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_launches_step_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d["dram_bytes_per_step"], os.path.relpath(files[-1], ROOT)
 
 
 def weights_file(tag="yolov3_416"):
@@ -260,6 +271,7 @@ def main_ours(args, rank, local_rank, world):
     if rank == 0:
         peaks = measured_peaks()
         conv_s, per = eng.time_convs(iters=3)
+        traffic, traffic_src = ncu_conv_traffic()
         flops_step = eng.conv_flops
         achieved = flops_step / conv_s / 1e12
         share = conv_s / (dt / args.steps)
@@ -278,7 +290,9 @@ def main_ours(args, rank, local_rank, world):
             "tensor_fraction_of_step": {"value": world * B * args.steps / dt / world * FLOPS_PER_IMAGE /
                                         (peaks["bf16_burst"] * 1e12), "of": f"{peaks['which']} burst bf16 peak"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                         "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+                         "traffic_note": f"DRAM read+write bytes of the conv launches of one step (ncu, {traffic_src}); "
+                                         "algorithmic: 161.3 MB/img activations x 64 + 124 MB weights = 10.4 GB",
                          "of": f"{peaks['which']} burst bf16 (kernel launches timed alone); "
                                f"sustained {peaks['bf16_sustained']}",
                          "kernel": f"conv_umma_kernel + conv_chain_kernel ({len(per)} launches/step cover the 75 "

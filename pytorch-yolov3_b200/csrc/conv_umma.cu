@@ -752,8 +752,9 @@ static int dispatch_epi(const y3_conv_desc* d, const void* x, const void* w, con
   // float32 head logits and the fused 2x upsample use the direct (register -> global) epilogue
   if (d->out_f32 || d->upsample2x || (d->flags & 2))
     return launch_conv<BLOCK_N, BLOCK_K, false, 1>(d, x, w, bias, residual, y, stream, force_im2col);
-  // wide tiles with a deep K loop: CTA pairs (cta_group::2).  flags bit2 forces single-CTA tiles.
-  if constexpr (BLOCK_N == 256 && BLOCK_K == 64) {
+  // 128- and 256-channel tiles: CTA pairs (cta_group::2) — each CTA stages only half of the weight slab,
+  // which is what the L2 -> SM path limits.  flags bit2 forces single-CTA tiles.
+  if constexpr ((BLOCK_N == 256 || BLOCK_N == 128) && BLOCK_K == 64) {
     const long long M = (long long)d->n * ((d->h + 2 * d->pad - d->ksize) / d->stride + 1) *
                         ((d->w + 2 * d->pad - d->ksize) / d->stride + 1);
     if (!(d->flags & 4) && M >= 2 * BLOCK_M)

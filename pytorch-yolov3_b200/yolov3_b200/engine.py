@@ -48,6 +48,7 @@ class Engine:
         self.conv_flops = 0  # algorithmic 2*MAC per batch, no padding credit
         self.conv_ops = []   # (block, launch closure, flops) for per-kernel timing in bench.py (uint8 programs)
         self.conv_ops_unfused_stem = []  # blocks 0-1 as separate launches (float32-input programs) when a stem exists
+        self.conv_info = {}  # block -> GEMM shape and algorithmic HBM bytes of the launch (tools/conv_report.py)
         # device "meta" builds the plan without touching a GPU (host-logic tests); it cannot run
         self.dry = torch.device(device).type == "meta"
         if self.dry:
@@ -259,6 +260,9 @@ class Engine:
                 flops = 2 * B * xin.H * xin.W * (32 * 64 + 64 * 32 * 9)
                 self.conv_flops += flops
                 self.conv_ops.append((i, fn, flops))
+                px = B * xin.H * xin.W
+                self.conv_info[i] = {"kind": "res chain 1x1+3x3+add", "M": px, "N": 64, "K": 64 + 9 * 32, "k": 3, "s": 1,
+                                     "bytes": px * 64 * 2 * 2 + (64 * 32 + 9 * 32 * 64) * 2}
                 done.add(i + 1)
             elif t == "convolutional":
                 xin = views[inputs_of(i)[0]]
@@ -307,6 +311,10 @@ class Engine:
                 cin_real = cin0 if inputs_of(i)[0] == INPUT else shape[inputs_of(i)[0]][0]
                 flops = 2 * B * ho * wo * cout * cin_real * k * k
                 self.conv_flops += flops
+                self.conv_info[i] = {"kind": "conv", "M": B * ho * wo, "N": cout, "K": cin_real * k * k, "k": k, "s": s,
+                                     "bytes": (B * xin.H * xin.W * xin.C * 2 + B * ho * wo * cout * (4 if head else 2)
+                                               * (4 if up else 1) + cout * cin_real * k * k * 2
+                                               + (B * ho * wo * cout * 2 if res else 0))}
                 if in_stem:
                     self.conv_ops_unfused_stem.append((i, fn, flops))
                 else:
@@ -319,6 +327,8 @@ class Engine:
                     emit("stem0", sfn, "stem_fused")
                     self.stem = sfn
                     self.conv_ops.insert(0, (0, sfn, sum(f for _, _, f in self.conv_ops_unfused_stem)))
+                    self.conv_info["stem"] = {"kind": "uint8 stem 3x3+3x3/2", "M": B * ho * wo, "N": 64, "K": 27 * 4 + 288,
+                                              "k": 3, "s": 2, "bytes": B * self.H * self.W * 3 + B * ho * wo * 64 * 2}
                 elif in_stem:
                     self._stem_w0 = self._stem_first_weights(bias)
                 if head:

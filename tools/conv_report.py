@@ -40,24 +40,14 @@ def main():
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
     total, per = eng.time_convs(iters=5)
     rows = []
-    blocks = net.blocks
-    cin_prev = {}
-    for (blk, sec, flops) in per:
-        b = blocks[blk]
-        v_out = eng.views[blk]
-        k, s = b["size"], b["stride"]
-        cout = b["filters"]
-        cin = flops // (2 * a.batch * (v_out.H // (2 if blocks[min(blk + 1, len(blocks) - 1)]["type"] == "upsample" else 1)) ** 2 * cout * k * k)
-        ho = v_out.H // (2 if blocks[min(blk + 1, len(blocks) - 1)]["type"] == "upsample" else 1)
-        M = a.batch * ho * ho
-        hin = ho * s
-        bytes_ = a.batch * hin * hin * max(cin, 16) * 2 + M * cout * (4 if v_out.f32 else 2) + cout * cin * k * k * 2
-        if blocks[min(blk + 1, len(blocks) - 1)]["type"] == "shortcut":
-            bytes_ += M * cout * 2
+    for n, (blk, sec, flops) in enumerate(per):
+        info = eng.conv_info["stem"] if (n == 0 and eng.stem is not None) else eng.conv_info[blk]
+        if eng.head_fused and info["kind"] == "conv" and blk + 1 < len(net.blocks) and net.blocks[blk + 1]["type"] == "yolo":
+            info = dict(info, kind="head conv + decode", bytes=info["bytes"] - info["M"] * info["N"] * 4)  # no logits written
         t_tensor = flops / (peaks["bf16_tflops"] * 1e12)
-        t_hbm = bytes_ / (peaks["hbm_gbs"] * 1e9)
-        rows.append({"block": blk, "M": M, "N": cout, "K": cin * k * k, "k": k, "s": s, "ms": sec * 1e3,
-                     "tflops": flops / sec / 1e12, "bound_ms": max(t_tensor, t_hbm) * 1e3,
+        t_hbm = info["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        rows.append({"block": blk, "kind": info["kind"], "M": info["M"], "N": info["N"], "K": info["K"], "k": info["k"],
+                     "s": info["s"], "ms": sec * 1e3, "tflops": flops / sec / 1e12, "bound_ms": max(t_tensor, t_hbm) * 1e3,
                      "bound": "tensor" if t_tensor > t_hbm else "hbm", "eff": max(t_tensor, t_hbm) / sec})
     out = {"cfg": a.cfg, "size": a.size, "batch": a.batch, "conv_ms": total * 1e3,
            "tflops": eng.conv_flops / total / 1e12, "bound_ms": sum(r["bound_ms"] for r in rows), "rows": rows}
@@ -68,7 +58,7 @@ def main():
     print(f"{'blk':>4} {'M':>9} {'N':>5} {'K':>5} k/s {'ms':>8} {'TF/s':>7} {'bound':>6} {'bnd_ms':>7} {'eff':>5}")
     for r in rows:
         print(f"{r['block']:>4} {r['M']:>9} {r['N']:>5} {r['K']:>5} {r['k']}/{r['s']} {r['ms']:>8.4f} {r['tflops']:>7.1f} "
-              f"{r['bound']:>6} {r['bound_ms']:>7.4f} {r['eff']:>5.2f}")
+              f"{r['bound']:>6} {r['bound_ms']:>7.4f} {r['eff']:>5.2f}  {r['kind'] if r['kind'] != 'conv' else ''}")
 
 
 if __name__ == "__main__":

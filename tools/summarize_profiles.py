@@ -38,24 +38,49 @@ def read_csv_after_header(path):
 
 
 def launches(src, dst):
+    """src: ncu --csv log with gpu__time_duration.sum (and optionally dram__bytes_read.sum /
+    dram__bytes_write.sum) per launch.  Also writes <dst stem>_traffic.json = DRAM bytes of the
+    convolution launches of the step (bench.py's roofline.traffic)."""
     rows = read_csv_after_header(src)
-    recs = [(short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3) for r in rows]
-    starts = [i for i, r in enumerate(recs) if "im2col" in r[0] or "pack" in r[0]]
+    by_id = collections.OrderedDict()
+    for r in rows:
+        e = by_id.setdefault(r["ID"], {"name": short(r["Kernel Name"]), "grid": r["Grid Size"], "block": r["Block Size"]})
+        val = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            e["us"] = val / 1e3 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1e3
+        elif r["Metric Name"].startswith("dram__bytes"):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            e[r["Metric Name"].split(".")[0].replace("dram__bytes_", "")] = val * scale
+    recs = list(by_id.values())
+    starts = [i for i, r in enumerate(recs) if "im2col" in r["name"] or "pack" in r["name"]
+              or r["name"].startswith("conv_chain_kernel<(int)0>") or r["name"].startswith("conv_chain_kernel<0>")]
     step = recs[starts[-1]:]
-    total = sum(r[3] for r in step)
+    total = sum(r["us"] for r in step)
+    has_dram = all("read" in r and "write" in r for r in step)
     agg = collections.OrderedDict()
-    for n, _, _, us in step:
-        a = agg.setdefault(n, [0.0, 0])
-        a[0] += us
+    for r in step:
+        a = agg.setdefault(r["name"], [0.0, 0, 0.0])
+        a[0] += r["us"]
         a[1] += 1
+        a[2] += (r.get("read", 0) + r.get("write", 0)) / 1e6
     with open(dst, "w") as f:
         f.write(f"# last step of {src}: {len(step)} launches, {total:.1f} us serialised (ncu, cold cache)\n")
-        f.write("# --- per-kernel aggregate: kernel,launches,us,share_of_step\n")
-        for n, (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-            f.write(f"{n},{c},{us:.1f},{us / total:.4f}\n")
-        f.write("# --- every launch: idx,kernel,grid,block,us\n")
-        for i, (n, g, b, us) in enumerate(step):
-            f.write(f"{i},{n},\"{g}\",\"{b}\",{us:.2f}\n")
+        f.write("# --- per-kernel aggregate: kernel,launches,us,share_of_step,dram_MB\n")
+        for n, (us, c, mb) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{n},{c},{us:.1f},{us / total:.4f},{mb:.1f}\n")
+        f.write("# --- every launch: idx,kernel,grid,block,us,dram_read_MB,dram_write_MB\n")
+        for i, r in enumerate(step):
+            f.write(f"{i},{r['name']},\"{r['grid']}\",\"{r['block']}\",{r['us']:.2f},"
+                    f"{r.get('read', 0) / 1e6:.2f},{r.get('write', 0) / 1e6:.2f}\n")
+    if has_dram:
+        import json
+        conv = [r for r in step if r["name"].startswith("conv_umma_kernel") or r["name"].startswith("conv_chain_kernel")]
+        out = {"source": dst, "conv_launches": len(conv),
+               "dram_bytes_per_step": sum(r["read"] + r["write"] for r in conv),
+               "conv_us_serialised": sum(r["us"] for r in conv), "step_us_serialised": total}
+        json.dump(out, open(dst.rsplit(".", 1)[0] + "_traffic.json", "w"), indent=1)
+        print(out)
     print(open(dst).read().split("# --- every")[0])
 
 
