@@ -14,14 +14,18 @@
 //   warp 1  : allocates TMEM; one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into one
 //             of two TMEM accumulator buffers; tcgen05.commit releases smem stages and
 //             publishes the finished accumulator.
-//   warps2-5: epilogue.  tcgen05.ld the accumulator (lane = output pixel), + folded-BN bias,
-//             LeakyReLU, + residual, convert to bf16.  STAGED form (the common one): each warp
-//             owns a swizzled smem staging slab for its 32 rows; the shortcut operand is
-//             TMA-loaded into the slab while the MMAs run, the result overwrites it in place and
-//             leaves through TMA stores (full-line writes, M tail clipped by the tensor map,
-//             ld_y pitch = channel slice of a concat buffer).  DIRECT form (float32 head
-//             logits, fused 2x upsample): registers -> st.global, one row per thread.
-// The double-buffered accumulator lets tile i's epilogue overlap tile i+1's MMAs.
+//   warps2-9: epilogue, two warps per TMEM lane quarter, each taking half of the tile's columns.
+//             tcgen05.ld the accumulator (lane = output pixel), + folded-BN bias (staged in smem
+//             once per tile), LeakyReLU, + residual, convert to bf16.  STAGED form (the common
+//             one): each warp owns 32 rows x its column blocks of a swizzled smem slab; the shortcut
+//             operand is TMA-loaded into the slab while the MMAs run, the result overwrites it in
+//             place and every finished 64-column block leaves at once through a TMA store
+//             (full-line writes, M tail clipped by the tensor map, ld_y pitch = channel slice of a
+//             concat buffer).  DIRECT form (float32 head logits, fused 2x upsample): registers ->
+//             st.global, one row per thread.
+// The double-buffered accumulator lets tile i's epilogue overlap tile i+1's MMAs.  Weights do not
+// depend on the previous layer: the producer requests the first ring pass of B tiles BEFORE the
+// programmatic-dependent-launch wait, so they stream in while the previous kernel drains.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "decode_math.cuh"
@@ -33,7 +37,7 @@ namespace y3 {
 
 static constexpr int BLOCK_M = 128;
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS = 320;  // 2 role warps + up to 8 epilogue warps (192 launched by default: 4)
 static constexpr int EPI_WARP0 = 2;  // first epilogue warp
 
 struct ConvKernelParams {
@@ -59,6 +63,7 @@ struct ConvKernelParams {
   uint4* cands;   // y3_cand records, [N][cap]
   int* counts;    // [N]
   int cap;
+  int trace;       // diagnostics only (Y3_CONV_TRACE=1): CTA 0 records its pipeline timeline
 };
 
 // One anchor of the fused YOLO-head epilogue.  The thread's pixel has its 255 logits in TMEM lane
@@ -166,14 +171,20 @@ struct ConvCfg {
   static constexpr int SLAB_BYTES = BLOCK_M * BLOCK_N * 2;
   static constexpr int STAGING_BUFS = BLOCK_N <= 128 ? 2 : 1;
   static constexpr int STAGING_BYTES = STAGED ? STAGING_BUFS * SLAB_BYTES : 0;
-  static constexpr int SMEM_LIMIT = 232448 - 1024 /*align slack*/ - 512 /*barriers*/;
+  // epilogue warps per TMEM lane quarter: 2 (each takes half of the columns) when the tile has at
+  // least two staged column blocks (STAGED) or 32 columns (direct / decode forms), otherwise 1
+  static constexpr int EPI_SPLIT = STAGED ? (EPI_BLOCKS >= 2 ? 2 : 1) : (BLOCK_N >= 32 ? 2 : 1);
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // this tile's bias, double-buffered
+  static constexpr int BAR_BYTES = 512;
+  // dynamic smem is declared __align__(1024): no alignment slack needed
+  static constexpr int SMEM_LIMIT = 232448 - BAR_BYTES - BIAS_BYTES;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;
-  static constexpr int MAX_STAGES = 16;  // barrier block: (2*STAGES + 9) * 8 bytes <= 512
+  static constexpr int MAX_STAGES = 16;  // barrier block: (2*STAGES + 13) * 8 + 8 bytes <= 512
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS_RAW = 2 * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
                                  : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES;
   // UMMA smem descriptor pieces (K-major, swizzle span = BLOCK_K*2 bytes)
   static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
   static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
@@ -182,6 +193,13 @@ struct ConvCfg {
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) |
                                     (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((BLOCK_M * CG) >> 4) << 24);
 };
+
+// Diagnostics (Y3_CONV_TRACE=1): CTA 0 records clock64() at the pipeline events of its first tiles;
+// read back with y3_debug_conv_trace (tools/conv_trace.py).  Slots: 0 entry, 1 set-up done, 2 PDL wait
+// passed, 3 first TMA issued, 8+2i / 9+2i MMA warp: operands of tile i landed / accumulator committed,
+// 32+4i.. epilogue warp 2: start, accumulator ready, drained, store issued; 80 stores drained, 81 exit.
+__device__ unsigned long long g_conv_trace[96];
+#define Y3_TRACE(slot) do { if (trace_on && (slot) < 96) g_conv_trace[(slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t desc_hi) {
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
@@ -198,22 +216,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tile_first = blockIdx.x / CG;   // persistent loop over tiles, one CTA (pair) per SM (pair)
   const int tile_step = gridDim.x / CG;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();  // the swizzled operand tiles need 1024-byte alignment
   const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024B-aligned
   const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
-  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], res[4], tmem_ptr
+  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], res[8], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto res_bar = [&](int q) { return bar_base + 8u * (2 * STAGES + 4 + q); };
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 8);
-  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 12);
+  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_base));
+  const uint32_t bias_base = bar_base + Cfg::BAR_BYTES;  // float [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const bool trace_on = p.trace && blockIdx.x == 0 && lane == 0;
+  // epilogue warps per TMEM lane quarter: launched with 10 warps -> the config's split, with 6 -> 1
+  const int split = blockDim.x == NUM_THREADS ? Cfg::EPI_SPLIT : 1;
+  if (warp == 0) Y3_TRACE(0);
 
   // PDL: the next kernel's CTAs may take this SM as soon as this CTA leaves; this CTA's own set-up
   // (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel.
@@ -231,9 +255,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp (of both CTAs)
+      ptx::mbar_init(tempty_bar(a), 4 * split * CG);  // one arrival per working epilogue warp (of both CTAs)
     }
-    for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
+    for (int q = 0; q < 8; ++q) ptx::mbar_init(res_bar(q), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -245,15 +269,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  pdl_wait();  // everything below reads or writes global memory the previous kernel may still own
+  if (warp == 0) Y3_TRACE(1);
+  // Programmatic dependent launch: only the threads that touch activations wait for the previous
+  // kernel (producer before its first A load, epilogue warps before their first residual load /
+  // store); weights and bias are constants and are requested before the wait.
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // One thread, and its instruction stream is on the critical path of every ring refill (a few
+    // extra instructions per k-block cost 3-6 % on the deep layers — measured): keep the loop minimal.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       // CG == 2: TMA completions of BOTH CTAs are counted on the leader's full barrier
       const uint32_t full_base = CG == 2 ? ptx::mapa(full_bar(0), 0) : full_bar(0);
+      const int b_row0 = (int)cta_rank * Cfg::B_ROWS;
+      // weights of the first ring pass do not depend on the previous layer: requested before the
+      // programmatic-dependent-launch wait (the ring is empty, no empty-barrier wait needed)
+      int pre = 0;
+      if (tile_first < num_tiles) {
+        pre = p.num_kb < STAGES ? p.num_kb : STAGES;
+        const int n_tile = tile_first % p.num_n_tiles;
+        for (int kb = 0; kb < pre; ++kb) {
+          const uint32_t fbar = full_base + 8u * kb;
+          if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(kb), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+          else ptx::mbar_arrive_cluster(fbar);
+          ptx::tma_load_2d<CG>(smem_base + kb * Cfg::STAGE_BYTES + Cfg::A_STRIDE, &tmap_b, fbar, kb * BLOCK_K,
+                               n_tile * BLOCK_N + b_row0);
+        }
+      }
+      pdl_wait();
+      Y3_TRACE(2);
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -264,25 +310,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int wo0 = rem - ho0 * p.Wo;
         const int w_base = wo0 * p.stride - p.pad;
         const int h_base = ho0 * p.stride - p.pad;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int b_row = n_tile * BLOCK_N + b_row0;
+        int r = 0, s = 0, cb = 0, kb = 0;
+        auto load_a = [&](uint32_t a_dst, uint32_t fbar) {
+          if (p.a_tiled) ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, m0);
+          else ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, w_base, h_base, img, (uint16_t)s, (uint16_t)r);
+          if (++cb == p.cin_blocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+        };
+        if (tile == tile_first) {  // barriers armed and B in flight (above): only A is missing
+          for (; kb < pre; ++kb) {
+            load_a(smem_base + stage * Cfg::STAGE_BYTES, full_base + 8u * stage);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          Y3_TRACE(3);
+        }
+        for (; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + Cfg::A_STRIDE;
           const uint32_t fbar = full_base + 8u * stage;
           if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
           else ptx::mbar_arrive_cluster(fbar);
-          if (p.a_tiled) {
-            ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, m0);
-          } else {
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, w_base, h_base, img, (uint16_t)s,
-                                        (uint16_t)r);
-          }
-          ptx::tma_load_2d<CG>(b_dst, &tmap_b, fbar, kb * BLOCK_K,
-                               n_tile * BLOCK_N + (int)cta_rank * Cfg::B_ROWS);
-          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          load_a(a_dst, fbar);
+          ptx::tma_load_2d<CG>(a_dst + Cfg::A_STRIDE, &tmap_b, fbar, kb * BLOCK_K, b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -302,6 +351,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+          if (kb == 0) Y3_TRACE(8 + 2 * it);
           ptx::tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_STRIDE;
@@ -317,16 +367,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete (signalled in both CTAs)
+        Y3_TRACE(9 + 2 * it);
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;               // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const int half = (warp - EPI_WARP0) >> 2;   // which half of the tile's columns (warps 2-5: 0, 6-9: 1)
     const int row = quarter * 32 + lane;
-    int it = 0;
+    const int e_tid = (warp - EPI_WARP0) * 32 + lane;
     // the accumulator is handed back on the LEADER's barrier (its MMA thread waits there)
     const uint32_t tempty_base = (CG == 2 && cta_rank != 0) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    if (half < split) {
+    int it = 0;
+    bool waited = false;  // griddepcontrol.wait executed (before the first access to activations)
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -342,105 +397,144 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // slab row r of column block cb lives at staging + cb*EPI_BLOCK_BYTES + r*EPI_SPAN; its
         // 16-byte units are XOR-swizzled exactly as CU_TENSOR_MAP_SWIZZLE_{128,64,32}B does.
         constexpr int SPAN = Cfg::EPI_SPAN;
+        const int CB_PER = Cfg::EPI_BLOCKS / split;  // column blocks of this warp
+        const int cb_first = half * CB_PER;
         const uint32_t swz = SPAN == 128 ? (row & 7) : SPAN == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);
         const uint32_t slab = staging_base + (Cfg::STAGING_BUFS == 2 ? (it & 1) * Cfg::SLAB_BYTES : 0);
         const uint32_t row_base = slab + row * SPAN;
         const uint32_t warp_base = slab + quarter * 32 * SPAN;
+        const uint32_t bias_s = bias_base + (it & 1) * (BLOCK_N * 4);
         const bool has_res = p.res != nullptr;
+        if (warp == EPI_WARP0) Y3_TRACE(32 + 4 * it);
+        // this tile's bias: global -> registers now, -> smem once the previous readers are past it
+        constexpr int BIAS_PER = (BLOCK_N + 127) / 128;  // values per thread with one warp per quarter
+        float bias_v[BIAS_PER];
+#pragma unroll
+        for (int j = 0; j < BIAS_PER; ++j) {
+          const int c = e_tid + j * split * 128;
+          bias_v[j] = c < BLOCK_N ? __ldg(p.bias + n0 + c) : 0.f;
+        }
+        if (!waited) { pdl_wait(); waited = true; }
         if (lane == 0) {
           // the TMA stores that last used this slab must have finished READING it before reuse
-          if (Cfg::STAGING_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (Cfg::STAGING_BUFS == 2 && CB_PER == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else if (Cfg::STAGING_BUFS == 2 && CB_PER == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           if (has_res) {
-            ptx::mbar_arrive_expect_tx(res_bar(quarter), 32 * BLOCK_N * 2);
-#pragma unroll
-            for (int cb = 0; cb < Cfg::EPI_BLOCKS; ++cb)
-              ptx::tma_load_2d(warp_base + cb * Cfg::EPI_BLOCK_BYTES, &tmap_r, res_bar(quarter),
-                               n0 + cb * Cfg::EPI_COLS, m0 + quarter * 32);
+            ptx::mbar_arrive_expect_tx(res_bar(warp - EPI_WARP0), 32 * CB_PER * Cfg::EPI_COLS * 2);
+            for (int cbi = 0; cbi < CB_PER; ++cbi)
+              ptx::tma_load_2d(warp_base + (cb_first + cbi) * Cfg::EPI_BLOCK_BYTES, &tmap_r, res_bar(warp - EPI_WARP0),
+                               n0 + (cb_first + cbi) * Cfg::EPI_COLS, m0 + quarter * 32);
           }
         }
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < BIAS_PER; ++j) {
+          const int c = e_tid + j * split * 128;
+          if (c < BLOCK_N) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * c), "f"(bias_v[j]) : "memory");
+        }
+        ptx::named_bar_sync(1, split * 128);  // bias visible to every epilogue warp (double-buffered by tile parity)
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        if (warp == EPI_WARP0) Y3_TRACE(33 + 4 * it);
         ptx::tc_fence_after();
-        if (has_res) ptx::mbar_wait(res_bar(quarter), it & 1);
+        if (has_res) ptx::mbar_wait(res_bar(warp - EPI_WARP0), it & 1);
 
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-          uint32_t v[16];
-          ptx::tmem_ld_x16(taddr + c0, v);
-          ptx::tmem_ld_wait();
-          float f[16];
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+        for (int cbi = 0; cbi < CB_PER; ++cbi) {
+          const int cb = cb_first + cbi;
+#pragma unroll 1
+          for (int cc = 0; cc < Cfg::EPI_COLS; cc += 16) {
+            const int c0 = cb * Cfg::EPI_COLS + cc;
+            uint32_t v[16];
+            ptx::tmem_ld_x16(taddr + c0, v);
+            float bz[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = __ldg(bias4 + q);
-            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-            f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-            f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
-          }
-          if (p.leaky) {
+            for (int q = 0; q < 4; ++q)
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bz[4 * q]), "=f"(bz[4 * q + 1]), "=f"(bz[4 * q + 2]),
+                           "=f"(bz[4 * q + 3]) : "r"(bias_s + 4u * (c0 + 4 * q)));
+            ptx::tmem_ld_wait();
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[j] > 0.f ? f[j] : 0.1f * f[j];
-          }
-          const int cb = c0 / Cfg::EPI_COLS;
-          const uint32_t u0 = uint32_t((c0 % Cfg::EPI_COLS) >> 3);  // 16-byte unit index in the row
-          const uint32_t a0 = row_base + cb * Cfg::EPI_BLOCK_BYTES + ((u0 ^ swz) << 4);
-          const uint32_t a1 = row_base + cb * Cfg::EPI_BLOCK_BYTES + (((u0 + 1) ^ swz) << 4);
-          if (has_res) {
-            uint4 r0, r1;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bz[j];
+            if (p.leaky) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 t = unpack_bf16x2(rr[j]);
-              f[2 * j] += t.x;
-              f[2 * j + 1] += t.y;
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.1f * f[j]);
             }
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pack_bf16x2(f[0], f[1])),
-                       "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pack_bf16x2(f[8], f[9])),
-                       "r"(pack_bf16x2(f[10], f[11])), "r"(pack_bf16x2(f[12], f[13])), "r"(pack_bf16x2(f[14], f[15])) : "memory");
-        }
-        // TMEM reads done: hand the accumulator back; publish the slab to the async proxy; store
-        ptx::tc_fence_before();
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
-          if (m0 + quarter * 32 < p.M) {
+            const uint32_t u0 = uint32_t(cc >> 3);  // 16-byte unit index in the row
+            const uint32_t a0 = row_base + cb * Cfg::EPI_BLOCK_BYTES + ((u0 ^ swz) << 4);
+            const uint32_t a1 = row_base + cb * Cfg::EPI_BLOCK_BYTES + (((u0 + 1) ^ swz) << 4);
+            if (has_res) {
+              uint4 r0, r1;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(a0));
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(a1));
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-            for (int cb = 0; cb < Cfg::EPI_BLOCKS; ++cb)
-              ptx::tma_store_2d(&tmap_y, warp_base + cb * Cfg::EPI_BLOCK_BYTES, n0 + cb * Cfg::EPI_COLS,
-                                m0 + quarter * 32);
+              for (int j = 0; j < 8; ++j) {
+                const float2 t = unpack_bf16x2(rr[j]);
+                f[2 * j] += t.x;
+                f[2 * j + 1] += t.y;
+              }
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pack_bf16x2(f[0], f[1])),
+                         "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7])) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pack_bf16x2(f[8], f[9])),
+                         "r"(pack_bf16x2(f[10], f[11])), "r"(pack_bf16x2(f[12], f[13])), "r"(pack_bf16x2(f[14], f[15])) : "memory");
           }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // this column block is complete: publish it to the async proxy and store it right away
+          if (cbi == CB_PER - 1) ptx::tc_fence_before();  // (all TMEM reads of this warp are done)
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (cbi == CB_PER - 1 && warp == EPI_WARP0) Y3_TRACE(34 + 4 * it);
+          if (lane == 0) {
+            if (cbi == CB_PER - 1) ptx::mbar_arrive_cluster(tempty_base + 8u * acc);  // hand the accumulator back
+            if (m0 + quarter * 32 < p.M)
+              ptx::tma_store_2d(&tmap_y, warp_base + cb * Cfg::EPI_BLOCK_BYTES, n0 + cb * Cfg::EPI_COLS, m0 + quarter * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
+        if (warp == EPI_WARP0) Y3_TRACE(35 + 4 * it);
       } else if constexpr (DECODE) {
         // ---- YOLO head: decode the pixel's three anchors straight from the accumulator ----
+        // The two warps of a lane quarter share a pixel's anchors 2:1, alternating with the tile parity
+        // (tile i: warps 2-5 take anchors 0,1 and warps 6-9 anchor 2; tile i+1 the other way round), so
+        // with the double-buffered accumulator both halves carry the same load.
         const bool valid = m < p.M;
         const int mm = valid ? m : 0;
         const int img = mm / p.HoWo;
         const int rem = mm - img * p.HoWo;
         const int grow = rem / p.Wo;
         const int gcol = rem - grow * p.Wo;
+        if (!waited) { pdl_wait(); waited = true; }
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
         float t[5], sum;
         int cls;
-        decode_anchor<0>(taddr, p, t, sum, cls);
-        emit_cand(p, 0, valid, img, grow, gcol, t, sum, cls, lane);
-        decode_anchor<1>(taddr, p, t, sum, cls);
-        emit_cand(p, 1, valid, img, grow, gcol, t, sum, cls, lane);
-        decode_anchor<2>(taddr, p, t, sum, cls);
-        emit_cand(p, 2, valid, img, grow, gcol, t, sum, cls, lane);
+        const bool two = split == 1 || ((it & 1) == half);  // this warp decodes two anchors of this tile
+        if (half == 0) {
+          decode_anchor<0>(taddr, p, t, sum, cls);
+          emit_cand(p, 0, valid, img, grow, gcol, t, sum, cls, lane);
+          if (two) {
+            decode_anchor<1>(taddr, p, t, sum, cls);
+            emit_cand(p, 1, valid, img, grow, gcol, t, sum, cls, lane);
+          }
+          if (split == 1) {
+            decode_anchor<2>(taddr, p, t, sum, cls);
+            emit_cand(p, 2, valid, img, grow, gcol, t, sum, cls, lane);
+          }
+        } else {
+          if (two) {
+            decode_anchor<1>(taddr, p, t, sum, cls);
+            emit_cand(p, 1, valid, img, grow, gcol, t, sum, cls, lane);
+          }
+          decode_anchor<2>(taddr, p, t, sum, cls);
+          emit_cand(p, 2, valid, img, grow, gcol, t, sum, cls, lane);
+        }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
       } else {
-        // ---- direct: registers -> global, one output row per thread ----
+        // ---- direct: registers -> global, one output row per thread, half of the columns per warp ----
+        const int COLS = BLOCK_N / split;
+        const int c_first = half * COLS;
         const bool valid = m < p.M;
         long long dst_pix = m;
         int up_w2 = 0;
@@ -454,10 +548,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const __nv_bfloat16* res_row = p.res ? p.res + (long long)m * p.ld_res + n0 : nullptr;
 
+        if (!waited) { pdl_wait(); waited = true; }
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        for (int c0 = c_first; c0 < c_first + COLS; c0 += 16) {
           uint32_t v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
           ptx::tmem_ld_wait();
@@ -518,7 +613,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_base + 8u * acc);
       }
     }
-    if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // smem must stay valid until the bulk stores have read it; their global writes complete with the grid
+    if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    if (warp == EPI_WARP0) Y3_TRACE(80);
   }
 
   ptx::tc_fence_before();
@@ -528,6 +626,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::tc_fence_after();
     ptx::tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
+  if (warp == 0) Y3_TRACE(81);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -675,6 +774,11 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   p.ld_out = d->ld_y; p.ld_res = d->ld_res;
   p.leaky = d->leaky; p.out_f32 = d->out_f32; p.upsample = d->upsample2x;
   p.orig_hw = nullptr; p.cands = nullptr; p.counts = nullptr; p.cap = 0;
+  {
+    static int trace = -1;
+    if (trace < 0) { const char* e = getenv("Y3_CONV_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
+    p.trace = trace;
+  }
   p.train_w = p.train_h = 1.f; p.prob_thresh = 0.f; p.box_offset = 0;
   for (int a = 0; a < 3; ++a) p.anchor_w[a] = p.anchor_h[a] = 0.f;
   if (DECODE) {
@@ -729,7 +833,12 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  // One epilogue warp per TMEM lane quarter by default; Y3_EPI_WARPS=8 launches two (each takes half of
+  // the columns).  Measured (profiles/r01d_notes.md): 8 warps shorten the 1x1 layers' drains by a few
+  // percent but slow the load-bound 3x3 layers by 3-5 % — their smem traffic competes with the MMA's.
+  static int epi_warps = -1;
+  if (epi_warps < 0) { const char* e = getenv("Y3_EPI_WARPS"); epi_warps = (e && atoi(e) == 8) ? 8 : 4; }
+  cfg.blockDim = dim3(epi_warps == 4 ? 192 : NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -800,6 +909,15 @@ static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, cons
 }
 
 }  // namespace y3
+
+// Diagnostics, not part of the ABI in include/: copy the trace of the last traced launch to the host.
+extern "C" int y3_debug_conv_trace(unsigned long long* out, int n) {
+  using namespace y3;
+  Y3_CHECK_ARG(out && n > 0 && n <= 96, "debug_conv_trace: n=%d", n);
+  Y3_CUDA_OK(cudaDeviceSynchronize());
+  Y3_CUDA_OK(cudaMemcpyFromSymbol(out, g_conv_trace, sizeof(unsigned long long) * n));
+  return Y3_OK;
+}
 
 extern "C" int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                                    const y3_head_desc* head, float prob_thresh, const int32_t* orig_hw,

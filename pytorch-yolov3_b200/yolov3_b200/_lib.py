@@ -14,7 +14,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_lon
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolov3_b200.so")
+# Y3_LIB: another build of the same ABI (A/B measurements of kernel changes on one box)
+LIB_PATH = os.environ.get("Y3_LIB") or os.path.join(_HERE, "libyolov3_b200.so")
 
 # Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
 EXPORTS = (

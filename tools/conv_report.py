@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--size", type=int, default=416)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv_report.json"))
+    ap.add_argument("--only", default="", help="comma-separated block numbers to time (default: all)")
     a = ap.parse_args()
     import yolov3_b200
     from tools.synth_weights import write_synthetic_weights
@@ -38,10 +39,13 @@ def main():
     torch.cuda.synchronize()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
+    if a.only:
+        keep = {int(b) for b in a.only.split(",")}
+        eng.conv_ops = [op for op in eng.conv_ops if op[0] in keep]
     total, per = eng.time_convs(iters=5)
     rows = []
     for n, (blk, sec, flops) in enumerate(per):
-        info = eng.conv_info["stem"] if (n == 0 and eng.stem is not None) else eng.conv_info[blk]
+        info = eng.conv_info["stem"] if (blk == 0 and eng.stem is not None) else eng.conv_info[blk]
         if eng.head_fused and info["kind"] == "conv" and blk + 1 < len(net.blocks) and net.blocks[blk + 1]["type"] == "yolo":
             info = dict(info, kind="head conv + decode", bytes=info["bytes"] - info["M"] * info["N"] * 4)  # no logits written
         t_tensor = flops / (peaks["bf16_tflops"] * 1e12)
