@@ -48,6 +48,7 @@ struct ConvKernelParams {
   int S;           // filter width
   int stride, pad;
   int num_m_tiles, num_n_tiles;
+  unsigned long long div_ntiles, div_howo, div_wo;  // ceil(2^48 / d): exact x / d for x * d < 2^48 (fast_div)
   int a_tiled;     // 1: A via 2-D tiled map (1x1, stride 1); 0: im2col map
   const float* bias;
   void* out;
@@ -201,6 +202,12 @@ struct ConvCfg {
 __device__ unsigned long long g_conv_trace[96];
 #define Y3_TRACE(slot) do { if (trace_on && (slot) < 96) g_conv_trace[(slot)] = clock64(); } while (0)
 
+// x / d through the precomputed reciprocal m = ceil(2^48 / d) (host: div_magic); exact while x * d < 2^48.
+__device__ __forceinline__ int fast_div(int x, unsigned long long m) {
+  return (int)__umul64hi((unsigned long long)(unsigned)x << 16, m);
+}
+static unsigned long long div_magic(int d) { return ((1ull << 48) + (unsigned long long)d - 1) / (unsigned long long)d; }
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t desc_hi) {
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
 }
@@ -279,7 +286,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // One thread, and its instruction stream is on the critical path of every ring refill (a few
     // extra instructions per k-block cost 3-6 % on the deep layers — measured): keep the loop minimal.
     if (lane == 0) {
-      int stage = 0;
       uint32_t phase = 0;
       // CG == 2: TMA completions of BOTH CTAs are counted on the leader's full barrier
       const uint32_t full_base = CG == 2 ? ptx::mapa(full_bar(0), 0) : full_bar(0);
@@ -289,7 +295,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int pre = 0;
       if (tile_first < num_tiles) {
         pre = p.num_kb < STAGES ? p.num_kb : STAGES;
-        const int n_tile = tile_first % p.num_n_tiles;
+        const int n_tile = tile_first - fast_div(tile_first, p.div_ntiles) * p.num_n_tiles;
         for (int kb = 0; kb < pre; ++kb) {
           const uint32_t fbar = full_base + 8u * kb;
           if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(kb), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
@@ -300,71 +306,100 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       pdl_wait();
       Y3_TRACE(2);
+      // ring position as running registers: stage address, full barrier (leader's, cluster address),
+      // own full barrier (expect_tx), empty barrier
+      uint32_t a_dst = smem_base, fbar = full_base, fbar_l = full_bar(0), ebar = empty_bar(0);
+      const uint32_t fbar_end = full_bar(STAGES);
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-        const int m_tile = tile / p.num_n_tiles;
+        // three divisions per tile, each a 64-bit multiply (a true division costs the ring ~600 idle cycles)
+        const int m_tile = fast_div(tile, p.div_ntiles);
         const int n_tile = tile - m_tile * p.num_n_tiles;
         const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M;
-        const int img = m0 / p.HoWo;
+        const int img = fast_div(m0, p.div_howo);
         const int rem = m0 - img * p.HoWo;
-        const int ho0 = rem / p.Wo;
+        const int ho0 = fast_div(rem, p.div_wo);
         const int wo0 = rem - ho0 * p.Wo;
         const int w_base = wo0 * p.stride - p.pad;
         const int h_base = ho0 * p.stride - p.pad;
         const int b_row = n_tile * BLOCK_N + b_row0;
-        int r = 0, s = 0, cb = 0, kb = 0;
-        auto load_a = [&](uint32_t a_dst, uint32_t fbar) {
-          if (p.a_tiled) ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, m0);
-          else ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, cb * BLOCK_K, w_base, h_base, img, (uint16_t)s, (uint16_t)r);
-          if (++cb == p.cin_blocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
-        };
+        int r = 0, s = 0, c = 0, kb = 0;  // filter tap (r, s), first channel of the K block, K block
+        const int cin = p.cin_blocks * BLOCK_K;
         if (tile == tile_first) {  // barriers armed and B in flight (above): only A is missing
           for (; kb < pre; ++kb) {
-            load_a(smem_base + stage * Cfg::STAGE_BYTES, full_base + 8u * stage);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (p.a_tiled) ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, c, m0);
+            else ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, c, w_base, h_base, img, (uint16_t)s, (uint16_t)r);
+            c += BLOCK_K;
+            if (c == cin) { c = 0; if (++s == p.S) { s = 0; ++r; } }
+            a_dst += Cfg::STAGE_BYTES; fbar += 8; fbar_l += 8; ebar += 8;
+            if (fbar_l == fbar_end) { a_dst = smem_base; fbar = full_base; fbar_l = full_bar(0); ebar = empty_bar(0); phase ^= 1u; }
           }
           Y3_TRACE(3);
         }
-        for (; kb < p.num_kb; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t fbar = full_base + 8u * stage;
-          if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), CG * (Cfg::A_BYTES + Cfg::B_BYTES));
-          else ptx::mbar_arrive_cluster(fbar);
-          load_a(a_dst, fbar);
-          ptx::tma_load_2d<CG>(a_dst + Cfg::A_STRIDE, &tmap_b, fbar, kb * BLOCK_K, b_row);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        int k0 = kb * BLOCK_K;  // K coordinate of the weight slab
+        if (p.a_tiled) {
+          for (; kb < p.num_kb; ++kb) {
+            ptx::mbar_wait(ebar, phase ^ 1u);
+            if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(fbar_l, CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+            else ptx::mbar_arrive_cluster(fbar);
+            ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, k0, m0);
+            ptx::tma_load_2d<CG>(a_dst + Cfg::A_STRIDE, &tmap_b, fbar, k0, b_row);
+            k0 += BLOCK_K;
+            a_dst += Cfg::STAGE_BYTES; fbar += 8; fbar_l += 8; ebar += 8;
+            if (fbar_l == fbar_end) { a_dst = smem_base; fbar = full_base; fbar_l = full_bar(0); ebar = empty_bar(0); phase ^= 1u; }
+          }
+        } else {
+          for (; kb < p.num_kb; ++kb) {
+            ptx::mbar_wait(ebar, phase ^ 1u);
+            if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(fbar_l, CG * (Cfg::A_BYTES + Cfg::B_BYTES));
+            else ptx::mbar_arrive_cluster(fbar);
+            ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, c, w_base, h_base, img, (uint16_t)s, (uint16_t)r);
+            ptx::tma_load_2d<CG>(a_dst + Cfg::A_STRIDE, &tmap_b, fbar, k0, b_row);
+            k0 += BLOCK_K;
+            c += BLOCK_K;
+            if (c == cin) { c = 0; if (++s == p.S) { s = 0; ++r; } }
+            a_dst += Cfg::STAGE_BYTES; fbar += 8; fbar_l += 8; ebar += 8;
+            if (fbar_l == fbar_end) { a_dst = smem_base; fbar = full_base; fbar_l = full_bar(0); ebar = empty_bar(0); phase ^= 1u; }
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // One thread; like the producer's, its instruction stream sits on the critical path whenever the
+    // ring runs dry (operands land -> MMAs must be issued at once), so everything is a running register.
     if (lane == 0 && cta_rank == 0) {
-      int stage = 0;
+      constexpr uint32_t DESC_STEP = Cfg::STAGE_BYTES >> 4;  // smem descriptor address field counts 16-byte units
+      const uint64_t desc_a0 = make_smem_desc(smem_base, Cfg::DESC_HI);
+      const uint64_t desc_b0 = make_smem_desc(smem_base + Cfg::A_STRIDE, Cfg::DESC_HI);
+      uint64_t desc_a = desc_a0, desc_b = desc_b0;
+      uint32_t fbar = full_bar(0), ebar = empty_bar(0);
+      const uint32_t fbar_end = full_bar(STAGES);
       uint32_t phase = 0;
       int it = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this buffer
+        Y3_TRACE(8 + 2 * it);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
-          if (kb == 0) Y3_TRACE(8 + 2 * it);
+        uint32_t accumulate = 0;  // the tile's first MMA overwrites the accumulator
+        for (int kb = p.num_kb; kb > 0; --kb) {
+          ptx::mbar_wait(fbar, phase);  // TMA bytes have landed
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + Cfg::A_STRIDE;
-          const uint64_t desc_a = make_smem_desc(a_addr, Cfg::DESC_HI);
-          const uint64_t desc_b = make_smem_desc(b_addr, Cfg::DESC_HI);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the swizzle span: +2 in the >>4 address field
-            ptx::umma_bf16_ss<CG>(tmem_d, desc_a + 2u * k, desc_b + 2u * k, Cfg::IDESC,
-                                  (kb | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_ss<CG>(tmem_d, desc_a + 2u * k, desc_b + 2u * k, Cfg::IDESC, accumulate);
+            accumulate = 1;
           }
-          ptx::umma_commit<CG>(empty_bar(stage));  // smem stage reusable (in both CTAs) once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          ptx::umma_commit<CG>(ebar);  // smem stage reusable (in both CTAs) once these MMAs retire
+          fbar += 8; ebar += 8; desc_a += DESC_STEP; desc_b += DESC_STEP;
+          if (fbar == fbar_end) {
+            fbar = full_bar(0); ebar = empty_bar(0); desc_a = desc_a0; desc_b = desc_b0;
+            phase ^= 1u;
+          }
         }
         ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete (signalled in both CTAs)
         Y3_TRACE(9 + 2 * it);
@@ -385,7 +420,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles;
+      const int m_tile = fast_div(tile, p.div_ntiles);
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = (m_tile * CG + (int)cta_rank) * BLOCK_M;
       const int m = m0 + row;
@@ -767,6 +802,9 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   p.stride = d->stride; p.pad = d->pad;
   p.num_m_tiles = (int)((M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
   p.num_n_tiles = d->cout / BLOCK_N;
+  p.div_ntiles = div_magic(p.num_n_tiles);
+  p.div_howo = div_magic(p.HoWo);
+  p.div_wo = div_magic(p.Wo);
   p.a_tiled = (d->ksize == 1 && d->stride == 1 && d->pad == 0 && !force_im2col) ? 1 : 0;
   p.bias = bias;
   p.out = y;
@@ -833,12 +871,14 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  // One epilogue warp per TMEM lane quarter by default; Y3_EPI_WARPS=8 launches two (each takes half of
-  // the columns).  Measured (profiles/r01d_notes.md): 8 warps shorten the 1x1 layers' drains by a few
-  // percent but slow the load-bound 3x3 layers by 3-5 % — their smem traffic competes with the MMA's.
+  // Epilogue warps per TMEM lane quarter (Y3_EPI_WARPS=4|8 forces one or two everywhere).  Measured on
+  // yolov3-416 x 64: two warps speed the decode / direct epilogues up by 10-20 % (register-heavy, long
+  // drains) and are neutral to slightly negative for the staged one on the load-bound 3x3 layers.
   static int epi_warps = -1;
-  if (epi_warps < 0) { const char* e = getenv("Y3_EPI_WARPS"); epi_warps = (e && atoi(e) == 8) ? 8 : 4; }
-  cfg.blockDim = dim3(epi_warps == 4 ? 192 : NUM_THREADS);
+  if (epi_warps < 0) { const char* e = getenv("Y3_EPI_WARPS"); epi_warps = e ? atoi(e) : 0; }
+  // default: the register-heavy direct / decode epilogues run two warps per quarter, the staged one one
+  const bool eight = epi_warps == 8 || (epi_warps != 4 && !STAGED);
+  cfg.blockDim = dim3(eight ? NUM_THREADS : 192);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
