@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -45,6 +48,89 @@ int num_sms() {
   return cached_sms;
 }
 
+// Host staging pool of y3_stage_images: parked worker threads (created once, never joined — the pool
+// is leaked on purpose so nothing is torn down under a waiting thread at process exit) copy 256 KB
+// chunks of the stacked batch handed out by an atomic counter; the caller copies along with them.
+class StagePool {
+ public:
+  void run(char* dst, const void* const* srcs, int n, long long bytes_each, int threads) {
+    const long long total = (long long)n * bytes_each;
+    const long long chunks = (total + kChunk - 1) / kChunk;
+    int helpers = (threads < 1 ? 1 : (threads > kMaxThreads ? kMaxThreads : threads)) - 1;
+    if (helpers > chunks - 1) helpers = (int)(chunks - 1);
+    std::unique_lock<std::mutex> call(call_mu_);  // one batch at a time
+    dst_ = dst; srcs_ = srcs; bytes_each_ = bytes_each; total_ = total; chunks_ = chunks;
+    next_.store(0, std::memory_order_relaxed);
+    if (helpers > 0) {
+      std::lock_guard<std::mutex> lk(mu_);
+      while ((int)workers_.size() < helpers) {
+        workers_.emplace_back(&StagePool::worker, this, (int)workers_.size());
+        workers_.back().detach();
+      }
+      wanted_ = helpers;
+      running_ = helpers;
+      ++generation_;
+    }
+    if (helpers > 0) cv_work_.notify_all();
+    copy_chunks();
+    if (helpers > 0) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_done_.wait(lk, [&] { return running_ == 0; });
+    }
+  }
+
+ private:
+  static constexpr long long kChunk = 256 << 10;
+  static constexpr int kMaxThreads = 16;
+
+  void copy_chunks() {
+    for (;;) {
+      const long long c = next_.fetch_add(1, std::memory_order_relaxed);
+      if (c >= chunks_) return;
+      long long off = c * kChunk;
+      long long left = total_ - off < kChunk ? total_ - off : kChunk;
+      while (left > 0) {  // a chunk may straddle images
+        const long long img = off / bytes_each_, in = off - img * bytes_each_;
+        const long long len = bytes_each_ - in < left ? bytes_each_ - in : left;
+        memcpy(dst_ + off, static_cast<const char*>(srcs_[img]) + in, (size_t)len);
+        off += len;
+        left -= len;
+      }
+    }
+  }
+
+  void worker(int index) {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return generation_ != seen && index < wanted_; });
+        seen = generation_;
+      }
+      copy_chunks();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--running_ == 0) cv_done_.notify_one();
+      }
+    }
+  }
+
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<std::thread> workers_;
+  unsigned long long generation_ = 0;
+  int wanted_ = 0, running_ = 0;
+  char* dst_ = nullptr;
+  const void* const* srcs_ = nullptr;
+  long long bytes_each_ = 0, total_ = 0, chunks_ = 0;
+  std::atomic<long long> next_{0};
+};
+
+StagePool& stage_pool() {
+  static StagePool* pool = new StagePool();
+  return *pool;
+}
+
 }  // namespace y3
 
 extern "C" {
@@ -68,20 +154,7 @@ int y3_check_device(int dev) {
 int y3_stage_images(void* dst, const void* const* srcs, int32_t n, int64_t bytes_each, int32_t threads) {
   Y3_CHECK_ARG(dst && srcs && n > 0 && bytes_each > 0, "stage_images: bad arguments");
   for (int i = 0; i < n; ++i) Y3_CHECK_ARG(srcs[i] != nullptr, "stage_images: image %d is null", i);
-  const long long total = (long long)n * bytes_each;
-  int t = threads < 1 ? 1 : (threads > 16 ? 16 : threads);
-  const long long by_size = total >> 21;  // a thread is worth starting for ~2 MB of copying
-  if (t > by_size) t = by_size < 1 ? 1 : (int)by_size;
-  if (t > n) t = n;
-  auto work = [=](int w) {
-    for (int i = w; i < n; i += t) memcpy(static_cast<char*>(dst) + (long long)i * bytes_each, srcs[i], (size_t)bytes_each);
-  };
-  if (t == 1) { work(0); return Y3_OK; }
-  std::vector<std::thread> pool;
-  pool.reserve(t - 1);
-  for (int w = 1; w < t; ++w) pool.emplace_back(work, w);
-  work(0);
-  for (auto& th : pool) th.join();
+  y3::stage_pool().run(static_cast<char*>(dst), srcs, n, bytes_each, threads);
   return Y3_OK;
 }
 
