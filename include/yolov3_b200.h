@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 4
+#define Y3_ABI_VERSION 5
 
 enum {
   Y3_OK = 0,
@@ -50,6 +50,14 @@ int y3_check_device(int dev);
  * since the last y3_reset_launch_count() (bench.py's "gpu_launches"). */
 long long y3_launch_count(void);
 void y3_reset_launch_count(void);
+/* Programmatic dependent launch (every kernel of the library is launched with the
+ * programmatic-stream-serialization attribute so that kernel i+1's prologue overlaps kernel i's
+ * tail).  on = 0 launches plain kernels instead: the better choice when several independent plans
+ * run on different streams at once, because a dependent CTA parked in griddepcontrol.wait holds an
+ * SM another plan's kernel could use.  Applies to subsequent launches (a captured CUDA graph keeps
+ * what was set at capture time).  Process-wide; returns the previous setting.  Default: on
+ * (off when the environment has Y3_NO_PDL=1). */
+int y3_set_pdl(int on);
 
 /* ---- a12: host-side staging of the image batch ---------------------------------------- */
 /* np.stack(images) of yolov3/inference.py:332 as n plain memcpy's into one (pinned) staging buffer,

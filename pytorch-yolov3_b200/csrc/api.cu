@@ -24,14 +24,16 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+static int g_pdl = -1;  // -1: not decided yet (environment), else y3_set_pdl's value
+
 bool pdl_enabled() {
-  static int cached = -1;
-  if (cached < 0) {
+  if (g_pdl < 0) {
     const char* e = getenv("Y3_NO_PDL");
-    cached = (e && e[0] == '1') ? 0 : 1;
+    g_pdl = (e && e[0] == '1') ? 0 : 1;
   }
-  return cached == 1;
+  return g_pdl == 1;
 }
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 int num_sms() {
   static int cached_dev = -1;
@@ -136,6 +138,12 @@ StagePool& stage_pool() {
 extern "C" {
 
 int y3_abi_version(void) { return Y3_ABI_VERSION; }
+
+int y3_set_pdl(int on) {
+  const int before = y3::pdl_enabled() ? 1 : 0;
+  y3::set_pdl(on);
+  return before;
+}
 
 const char* y3_last_error(void) { return y3::g_err; }
 

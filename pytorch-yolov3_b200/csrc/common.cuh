@@ -50,7 +50,8 @@ int encode_tiled_map(void* map, int rank, const void* base, const uint64_t* dims
                      const uint32_t* box, int swizzle_bytes);
 
 int num_sms();  // SM count of the current device (cached per device)
-bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 turns it off)
+bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 / y3_set_pdl(0) turn it off)
+void set_pdl(int on);
 
 #ifdef __CUDACC__
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute:

@@ -19,13 +19,13 @@ LIB_PATH = os.environ.get("Y3_LIB") or os.path.join(_HERE, "libyolov3_b200.so")
 
 # Symbols include/yolov3_b200.h declares (tests check the .so exports exactly these).
 EXPORTS = (
-    "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count",
+    "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count", "y3_set_pdl",
     "y3_stage_images", "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
 )
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class ConvDesc(ctypes.Structure):
@@ -139,6 +139,11 @@ def launch_count():
 
 def reset_launch_count():
     lib().y3_reset_launch_count()
+
+
+def set_pdl(on):
+    """Programmatic dependent launch for subsequent launches / graph captures; returns the previous setting."""
+    return bool(lib().y3_set_pdl(1 if on else 0))
 
 
 def stage_images(dst, images, threads):

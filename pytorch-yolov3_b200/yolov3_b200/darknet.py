@@ -232,14 +232,16 @@ class Darknet(torch.nn.Module):
                 dev = p.device
         return _lib.require_device(dev)
 
-    def engine(self, batch, height, width, slot=0):
+    def engine(self, batch, height, width, slot=0, concurrent=False):
         """The compiled execution plan for this input geometry (built on first use).  ``slot`` > 0
         gives further independent instances (own buffers and graphs) of the same geometry:
-        ``inference`` pipelines sub-batches through several of them."""
+        ``inference`` pipelines sub-batches through several of them.  ``concurrent`` (honoured when
+        the plan is first built) marks a plan that runs next to others on different streams: its
+        graphs are captured without programmatic dependent launch (see ``y3_set_pdl``)."""
         key = (batch, height, width) if slot == 0 else (batch, height, width, slot)
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self, batch, height, width, self._target_device())
+            eng = Engine(self, batch, height, width, self._target_device(), pdl=not concurrent)
             self._engines[key] = eng
         return eng
 

@@ -41,8 +41,10 @@ class View:
 
 
 class Engine:
-    def __init__(self, net, batch, height, width, device):
+    def __init__(self, net, batch, height, width, device, pdl=True):
         self.net, self.B, self.H, self.W, self.device = net, batch, height, width, device
+        # programmatic dependent launch in this plan's graphs (off for plans that run concurrently)
+        self.pdl = pdl and os.environ.get("Y3_NO_PDL", "0") != "1"
         self.use_graphs = os.environ.get("Y3_NO_GRAPH", "0") != "1"
         self._graphs = {}
         self.conv_flops = 0  # algorithmic 2*MAC per batch, no padding credit
@@ -590,6 +592,7 @@ class Engine:
             fn = self._program(key)
             with torch.cuda.device(self.device):
                 _lib.reset_launch_count()
+                pdl_before = _lib.set_pdl(self.pdl)
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
@@ -602,6 +605,7 @@ class Engine:
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         fn()
+                _lib.set_pdl(pdl_before)
             ent = (fn, graph, launches)
             self._graphs[key] = ent
         fn, graph, _ = ent

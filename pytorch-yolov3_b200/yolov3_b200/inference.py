@@ -137,7 +137,7 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
     spans = _sub_batches(B)
     io = net.__dict__.setdefault("_host_io", {}).get((B, H, W, str(dev)))
     if io is None:
-        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if len(spans) > 1 else 0)
+        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if len(spans) > 1 else 0, concurrent=len(spans) > 1)
         if eng0.device != dev:
             raise RuntimeError(f"net runs on {eng0.device}, inference(device='{device}') requested")
         with torch.cuda.device(dev):
@@ -145,7 +145,7 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
             io = {"img": _pinned((B, H, W, 3), torch.uint8), "hw": _pinned((B, 2), torch.int32),
                   "meta": [_pinned((2, hi - lo, C), torch.int32) for lo, hi in spans],
                   "dst": [_pinned((hi - lo, C), torch.int32) for lo, hi in spans],
-                  "engines": [net.engine(hi - lo, H, W, slot=(k + 1) if len(spans) > 1 else 0)
+                  "engines": [net.engine(hi - lo, H, W, slot=(k + 1) if len(spans) > 1 else 0, concurrent=len(spans) > 1)
                               for k, (lo, hi) in enumerate(spans)],
                   "streams": [torch.cuda.Stream(device=dev) for _ in spans] if len(spans) > 1 else [None],
                   "out": (torch.empty(B * M, 4, device=dev, dtype=torch.int64),

@@ -186,7 +186,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.y3_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.y3_abi_version() == _lib.ABI_VERSION == 5
     lib.y3_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.y3_last_error(), bytes)
 

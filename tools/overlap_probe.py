@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--splits", default="1,2,4")
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--alternate", type=int, default=0,
+                    help="N > 1: N full-batch plans on N streams, consecutive steps alternate between them "
+                         "(step i+1's convolutions can fill the SMs step i's decode / NMS leave idle)")
     args = ap.parse_args()
     import bench
     import yolov3_b200
@@ -36,6 +39,38 @@ def main():
     imgs = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (B, 416, 416, 3), dtype=np.uint8)).to(dev)
     key = ("det_u8", bench.PROB_THRESH, bench.IOU_THRESH)
     main_s = torch.cuda.Stream()
+    if args.alternate > 1:
+        N = args.alternate
+        prio = [0] * N
+        engs = [net.engine(B, 416, 416, slot=100 + k) for k in range(N)]
+        streams = [torch.cuda.Stream(priority=p) for p in prio]
+        for e in engs:
+            e.in_u8.copy_(imgs)
+            e.orig_hw.copy_(torch.tensor([[416, 416]] * B, dtype=torch.int32))
+            e.launch(key)
+        torch.cuda.synchronize()
+
+        def run(n):
+            for st in streams:
+                st.wait_stream(main_s)
+            for i in range(n):
+                with torch.cuda.stream(streams[i % N]):
+                    engs[i % N].launch(key)
+            for st in streams:
+                main_s.wait_stream(st)
+
+        with torch.cuda.stream(main_s):
+            run(2 * N)
+            main_s.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main_s)
+            run(args.iters)
+            e1.record(main_s)
+            main_s.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        print(f"alternate {N}: {ms:.3f} ms per {B} images, {B / ms * 1e3:.0f} images/s "
+              f"(PDL {'off' if os.environ.get('Y3_NO_PDL') == '1' else 'on'})", flush=True)
+        return
     for S in [int(s) for s in args.splits.split(",")]:
         n = B // S
         engs = [net.engine(n, 416, 416, slot=10 * S + k) for k in range(S)]
