@@ -49,6 +49,11 @@ void count_launch(int n = 1);
 int encode_tiled_map(void* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes);
 
+// 3x3 / stride 1 / pad 1 layers whose tiles stay >= 93 % full in the row-padded virtual space run on the
+// shared-memory-patch kernel (conv_patch.cu); returns -1 when the layer should use the im2col kernel.
+int conv3x3_patch_try(const ::y3_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                      void* y, cudaStream_t stream);
+
 int num_sms();  // SM count of the current device (cached per device)
 bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 / y3_set_pdl(0) turn it off)
 void set_pdl(int on);

@@ -868,8 +868,7 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = num_sms() / CG;  // CTAs (or CTA pairs) resident at once
   const int grid = CG * (num_tiles < slots ? num_tiles : slots);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   // Epilogue warps per TMEM lane quarter (Y3_EPI_WARPS=4|8 forces one or two everywhere).  Measured on
   // yolov3-416 x 64: two warps speed the decode / direct epilogues up by 10-20 % (register-heavy, long
@@ -943,6 +942,10 @@ static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, cons
                (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                "conv: pointers must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!force_im2col) {  // 3x3 / 1 layers on large feature maps: input patch in smem, nine taps = nine descriptor offsets
+    const int rc = conv3x3_patch_try(d, x, w, bias, residual, y, s);
+    if (rc >= 0) return rc;
+  }
   if (d->cin % 64 == 0) return dispatch_n<64>(d, x, w, bias, residual, y, s, force_im2col);
   if (d->cin % 32 == 0) return dispatch_n<32>(d, x, w, bias, residual, y, s, force_im2col);
   return dispatch_n<16>(d, x, w, bias, residual, y, s, force_im2col);

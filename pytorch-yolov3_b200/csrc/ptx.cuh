@@ -96,13 +96,22 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
 }
 // 4-D tiled load over an NHWC tensor, coordinates (c, w, h, n); out-of-range elements are zero-filled
 // (negative coordinates allowed) — used to fetch a spatial patch with its halo in one request.
+template <int CG = 1>
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c,
                                             int32_t w, int32_t h, int32_t n) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
-      : "memory");
+  if constexpr (CG == 2) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+        : "memory");
+  }
 }
 // 4-D tiled store of a (c, w, h, n) box (elements outside the tensor are clipped).
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int32_t c, int32_t w,
