@@ -265,6 +265,9 @@ def main_ours(args, rank, local_rank, world):
     for i in range(5):  # every one of the four rotating batches once: pinned result buffers reach steady state
         yolov3_b200.inference(net, host_lists[i % 4], device=str(dev), prob_thresh=PROB_THRESH,
                               nms_iou_thresh=IOU_THRESH, resize=False)
+        if world > 1:  # NCCL sets its point-to-point channels up on the first gather: not part of a step
+            from yolov3_b200.inference import last_device_outputs
+            ydist.gather_outputs(*last_device_outputs(net, B, SIZE, SIZE, dev))
     barrier()
     t0 = time.perf_counter()
     d2h = 0
