@@ -54,7 +54,6 @@ struct PatchParams {
   const __nv_bfloat16* res;
   int ld_out, ld_res;
   int leaky;
-  int dbg;  // diagnostics (Y3_PATCH_DBG): 1 no stores, 2 no residual loads
 };
 
 __device__ __forceinline__ int pt_div(int x, unsigned long long m) {
@@ -274,7 +273,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int c_first = half * Cfg::COLS;
     constexpr int NBLK = Cfg::COLS / 64;       // 64-column blocks of this warp
     const uint32_t tempty0 = (CG == 2 && cta_rank != 0) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
-    const bool has_res = p.res != nullptr && !(p.dbg & 2);
+    const bool has_res = p.res != nullptr;
     // this warp's transpose tile: 32 rows x 128 bytes, 16-byte units XOR-swizzled by (row & 7)
     const uint32_t stg = stg_base + (uint32_t)(warp - 2) * 4096u;
     const uint32_t own_row = stg + (uint32_t)lane * 128u;                 // this thread's row (it owns TMEM lane `row`)
@@ -375,7 +374,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const uint32_t ad = stg + r_ * 128u + (((uint32_t)t_unit ^ (r_ & 7u)) << 4);
           uint4 o;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(ad));
-          if (m_t[i] >= 0 && !(p.dbg & 1))
+          if (m_t[i] >= 0)
             st_16(p.out + (long long)m_t[i] * p.ld_out + n0 + c_first + 64 * b + 8 * t_unit, o);
         }
         __syncwarp();  // the tile is overwritten by the next block / tile
@@ -460,7 +459,6 @@ static int launch_patch(const y3_conv_desc* d, const void* x, const void* w, con
   p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.ld_out = d->ld_y; p.ld_res = d->ld_res;
   p.leaky = d->leaky;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("Y3_PATCH_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
 
   alignas(64) CUtensorMap tmap_x, tmap_b;
   {

@@ -226,18 +226,31 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
 
 
 def _sub_batches(batch):
-    """Contiguous spans ``inference`` pipelines through the GPU: 4 for batches of 32 and more, 2 from
-    16, otherwise the whole batch (``Y3_SUB_BATCHES`` overrides the count)."""
+    """Contiguous spans ``inference`` pipelines through the GPU.  The upload of the FIRST span and the
+    download of the LAST one are the only transfers nothing hides, while small plans use the GPU less
+    well, so the spans grow: 1/8, 3/8, 1/2 of the batch from 32 images, two halves from 16, otherwise
+    the whole batch.  ``Y3_SUB_BATCHES=n`` forces n equal spans, ``Y3_SUB_SPLIT=a,b,c`` explicit sizes
+    (scaled to the batch)."""
     import os
-    n = int(os.environ.get("Y3_SUB_BATCHES", "0")) or (4 if batch >= 32 else 2 if batch >= 16 else 1)
-    n = max(1, min(n, batch))
-    base, rem = divmod(batch, n)
-    spans, lo = [], 0
-    for k in range(n):
-        hi = lo + base + (1 if k < rem else 0)
-        spans.append((lo, hi))
-        lo = hi
-    return spans
+    split = os.environ.get("Y3_SUB_SPLIT", "")
+    n = int(os.environ.get("Y3_SUB_BATCHES", "0"))
+    if split:
+        parts = [float(x) for x in split.split(",")]
+    elif n:
+        parts = [1.0] * max(1, min(n, batch))
+    elif batch >= 32:
+        parts = [1.0, 3.0, 4.0]
+    elif batch >= 16:
+        parts = [1.0, 1.0]
+    else:
+        parts = [1.0]
+    total = sum(parts)
+    edges, acc = [0], 0.0
+    for p_ in parts:
+        acc += p_
+        edges.append(min(batch, max(edges[-1], int(round(batch * acc / total)))))
+    edges[-1] = batch
+    return [(lo, hi) for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo]
 
 
 def last_device_outputs(net, batch, height, width, device):

@@ -116,6 +116,47 @@ def test_conv_fused_shortcut_upsample_and_concat_slice():
     assert torch.equal(got[:, :, 0::2, 0::2], got[:, :, 1::2, 1::2])
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,res,slice_", [
+    (2, 52, 52, 128, 256, True, False),    # the yolov3-416 52x52 residual-unit shape
+    (1, 38, 38, 64, 256, False, False),    # yolov3-spp 608: 38x38, tiles 94 % full
+    (3, 49, 50, 64, 512, True, True),      # odd extents, two n tiles, output is a channel slice of a wider buffer
+    (2, 40, 130, 64, 256, True, False),    # padded row (132) longer than a CTA's 128 positions: patches do not fit, im2col fallback
+])
+def test_conv_patch_kernel_equals_im2col_kernel_and_oracle(n, H, W, cin, cout, res, slice_):
+    """conv_patch.cu (3x3/1 on large maps, input patch in smem, row-padded virtual positions) against
+    conv_umma.cu's im2col path forced by flags bit0, and both against torch fp32 on the bf16 inputs.
+    Same products, different K order (channel block outer vs tap outer): equal up to fp32 summation
+    order, i.e. to one bf16 ulp of the output."""
+    g = torch.Generator().manual_seed(1000 + H * W + cout)
+    x = torch.randn(n, cin, H, W, generator=g)
+    prm = {"weight": torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5,
+           "bias": torch.randn(cout, generator=g) * 0.1}
+    r = torch.randn(n, cout, H, W, generator=g)
+    w, b = fold(prm, cin, cout)
+    xb, rb = nhwc_bf16(x), nhwc_bf16(r)
+    ld_y = cout + 64 if slice_ else cout
+    c0 = 32 if slice_ else 0
+    outs = []
+    for force_im2col in (False, True):
+        buf = torch.zeros(n, H, W, ld_y, device=dev(), dtype=torch.bfloat16)
+        _lib.conv2d(xb.data_ptr(), w, b, buf.data_ptr() + c0 * 2, n=n, h=H, w_in=W, cin=cin, cout=cout, ksize=3,
+                    stride=1, pad=1, ld_x=cin, ld_y=ld_y, leaky=True, res_ptr=rb.data_ptr() if res else None,
+                    ld_res=cout if res else 0, force_im2col=force_im2col)
+        torch.cuda.synchronize()
+        outs.append(buf.float().cpu())
+    got_patch, got_im2col = outs
+    ref = F.leaky_relu(F.conv2d(xb.float().cpu().permute(0, 3, 1, 2), prm["weight"].bfloat16().float(), prm["bias"],
+                                padding=1), 0.1)
+    if res:
+        ref = ref + rb.float().cpu().permute(0, 3, 1, 2)
+    for got in outs:
+        assert rel_err(got[..., c0:c0 + cout].permute(0, 3, 1, 2), ref) <= CONV_TOL
+        if slice_:  # channels outside the slice untouched
+            assert float(got[..., :c0].abs().max()) == 0 and float(got[..., c0 + cout:].abs().max()) == 0
+    d = (got_patch - got_im2col).abs()
+    assert float(d.max()) <= 2.0 ** -7 * float(got_im2col.abs().max())  # one bf16 ulp at the top of the range
+
+
 def test_conv_rejects_bad_arguments():
     t = torch.zeros(16, device=dev(), dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="cin"):
