@@ -75,7 +75,7 @@ def launches(src, dst):
                     f"{r.get('read', 0) / 1e6:.2f},{r.get('write', 0) / 1e6:.2f}\n")
     if has_dram:
         import json
-        conv = [r for r in step if r["name"].startswith("conv_umma_kernel") or r["name"].startswith("conv_chain_kernel")]
+        conv = [r for r in step if r["name"].startswith(("conv_umma_kernel", "conv_chain_kernel", "conv_patch_kernel"))]
         out = {"source": dst, "conv_launches": len(conv),
                "dram_bytes_per_step": sum(r["read"] + r["write"] for r in conv),
                "conv_us_serialised": sum(r["us"] for r in conv), "step_us_serialised": total}
