@@ -227,3 +227,53 @@ def test_u8_scale_by_reciprocal_is_exact_after_bf16_rounding():
     v = torch.arange(256, dtype=torch.float32)
     assert torch.equal((v / 255.0).bfloat16(), (v * np.float32(0.003921568859368563)).bfloat16())
     assert np.float32(0.003921568859368563) == np.float32(1.0) / np.float32(255.0)
+
+
+def test_sub_batch_spans_cover_the_batch_in_order(monkeypatch):
+    """inference() pipelines contiguous spans through the GPU: whatever the layout (default growing
+    spans, forced equal spans, explicit split), the spans tile [0, batch) without gaps or empties."""
+    from yolov3_b200.inference import _sub_batches
+    for env in ({}, {"Y3_SUB_BATCHES": "4"}, {"Y3_SUB_BATCHES": "1"}, {"Y3_SUB_SPLIT": "1,3,4"}, {"Y3_SUB_SPLIT": "5,1,1,9"}):
+        monkeypatch.delenv("Y3_SUB_BATCHES", raising=False)
+        monkeypatch.delenv("Y3_SUB_SPLIT", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for batch in list(range(1, 70)) + [100, 127, 128, 256]:
+            spans = _sub_batches(batch)
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(hi > lo for lo, hi in spans)
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    monkeypatch.delenv("Y3_SUB_SPLIT", raising=False)
+    assert _sub_batches(64) == [(0, 8), (8, 32), (32, 64)]  # small first upload, the rest in two large plans
+    assert _sub_batches(8) == [(0, 8)]
+
+
+def test_stage_images_equals_np_stack_for_any_thread_count():
+    """y3_stage_images (host threads of the library copying 256 KB chunks that may straddle images)
+    is np.stack, for odd image sizes, more threads than chunks and repeated use of the parked pool."""
+    rng = np.random.default_rng(5)
+    for shape, n in (((37, 53, 3), 5), ((416, 416, 3), 16), ((600, 701, 3), 3), ((1, 1, 3), 2)):
+        imgs = [rng.integers(0, 256, shape, dtype=np.uint8) for _ in range(n)]
+        want = np.stack(imgs)
+        for threads in (1, 3, 16, 64):
+            dst = np.zeros_like(want)
+            _lib.stage_images(dst, imgs, threads)
+            assert np.array_equal(dst, want)
+
+
+def test_reciprocal_division_is_exact_over_the_kernels_ranges():
+    """The convolution kernels replace x / d by umulhi(x << 16, ceil(2^48 / d)) (conv_umma.cu fast_div,
+    conv_patch.cu pt_div).  Exact whenever x * d < 2^48: checked here on the divisors the plans use
+    (feature-map sizes, tiles per image, n tiles) at the largest x they see, plus random pairs."""
+    def fast_div(x, d):
+        m = ((1 << 48) + d - 1) // d
+        return ((x << 16) * m) >> 64
+    rng = np.random.default_rng(11)
+    divisors = [1, 2, 3, 4, 8, 11, 13, 15, 19, 26, 28, 38, 40, 44, 52, 54, 76, 104, 106, 152, 169, 208, 304, 361, 416,
+                608, 676, 1444, 2704, 5776, 10816, 23104, 43264, 92416, 173056, 369664]
+    for d in divisors:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1 if d < (1 << 17) else (1 << 28)]
+        xs += [int(v) for v in rng.integers(0, min(1 << 31, (1 << 48) // d), 2000)]
+        for x in xs:
+            if x * d < (1 << 48):
+                assert fast_div(x, d) == x // d, (x, d)
