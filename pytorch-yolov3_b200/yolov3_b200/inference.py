@@ -19,6 +19,9 @@ import torch
 from . import _lib
 
 _TRACE = os.environ.get("Y3_TRACE", "0") == "1"
+# host threads that stage a batch into pinned memory: the box's cores shared between the ranks of a node
+# (torchrun exports LOCAL_WORLD_SIZE), at most 16 — beyond that the copy is memory-bound
+_STAGE_THREADS = max(2, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 
 def cxywh_to_tlbr(bbox_xywh):
@@ -93,7 +96,7 @@ def _stack_into(dst, images):
     """``np.stack(images)`` straight into the pinned staging buffer: plain memcpy's on a few host
     threads of the library (no interpreter lock held); non-contiguous inputs are compacted first."""
     images = [im if im.flags.c_contiguous else np.ascontiguousarray(im) for im in images]
-    _lib.stage_images(dst, images, min(16, os.cpu_count() or 1))
+    _lib.stage_images(dst, images, _STAGE_THREADS)
 
 
 def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True):
