@@ -17,7 +17,9 @@
 //     absolute smem address, so a row-shifted descriptor start is legal — same property
 //     conv_chain.cu relies on).  In a CTA pair (cta_group::2) both CTAs must present their rows at
 //     the SAME smem offset, so the peer lands its patch shifted by (off_leader - off_peer) rows.
-//   * Weights stream through their own ring, one 64-channel tap slab per stage.
+//   * Weights stream through their own ring, one 64-channel tap slab per stage; patches and weights
+//     have a producer thread each, so a patch is requested one unit ahead of the MMAs whatever the
+//     state of the weight ring.
 //   * Epilogue: one thread per virtual position (its TMEM lane); dummies (wp >= W, v >= H * Wp) are
 //     dropped.  A row's pixels are not consecutive in the dense output any more, so TMA boxes do not
 //     apply; every warp transposes 32 rows x 64 columns through a 4 KB swizzled smem tile instead, so
@@ -36,7 +38,7 @@ namespace y3 {
 
 static constexpr int PT_BLOCK_M = 128;
 static constexpr int PT_BLOCK_K = 64;
-static constexpr int PT_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
+// warps: patch producer, MMA issuer, 4 * EW epilogue warps (EW per TMEM lane quarter), weight producer
 static constexpr int PT_MAX_B_STAGES = 12;
 
 struct PatchParams {
@@ -67,9 +69,15 @@ struct PatchCfg {
   static constexpr int B_BYTES = B_ROWS * PT_BLOCK_K * 2;
   static constexpr int BAR_BYTES = 512;   // (2 * 12 + 2 + 2 + 2 + 2) barriers * 8 + tmem pointer
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;
-  static constexpr int STG_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 64 columns bf16, swizzled
+  // two epilogue warps per TMEM lane quarter for 256-channel tiles; one for 128-channel tiles, whose
+  // 8 KB weight stages need every byte the transpose tiles can spare to keep the ring deep enough
+  static constexpr int EW = BLOCK_N >= 256 ? 2 : 1;
+  static constexpr int EPI_THREADS = 128 * EW;
+  static constexpr int THREADS = 64 + EPI_THREADS + 32;
+  static constexpr int WEIGHT_WARP = 2 + 4 * EW;
+  static constexpr int STG_BYTES = 4 * EW * 4096;  // per epilogue warp: 32 rows x 64 columns bf16, swizzled
   static constexpr int TMEM_COLS = 2 * BLOCK_N <= 256 ? 256 : 512;
-  static constexpr int COLS = BLOCK_N / 2;  // columns per epilogue warp (two warps per TMEM lane quarter)
+  static constexpr int COLS = BLOCK_N / (BLOCK_N >= 256 ? 2 : 1);  // columns per epilogue warp
   // K-major, 128B swizzle: SBO = 8 rows * 128 B, layout type 2
   static constexpr uint64_t DESC_HI = ((uint64_t(1024) >> 4) << 32) | (1ull << 46) | (2ull << 61);
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
@@ -81,7 +89,7 @@ __device__ __forceinline__ uint64_t pt_desc(uint32_t smem_addr, uint64_t hi) {
 }
 
 template <int BLOCK_N, int CG>
-__global__ void __launch_bounds__(PT_THREADS, 1)
+__global__ void __launch_bounds__(PatchCfg<BLOCK_N, CG>::THREADS, 1)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                   const PatchParams p) {
   using Cfg = PatchCfg<BLOCK_N, CG>;
@@ -122,7 +130,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       ptx::mbar_init(pfull_bar(b), CG);
       ptx::mbar_init(pempty_bar(b), 1);
       ptx::mbar_init(tfull_bar(b), 1);
-      ptx::mbar_init(tempty_bar(b), 8 * CG);  // one arrival per epilogue warp (of both CTAs)
+      ptx::mbar_init(tempty_bar(b), 4 * Cfg::EW * CG);  // one arrival per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
@@ -167,14 +175,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   };
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
+    // ===================== TMA producer: input patches (one thread) =====================
+    // Patches and weights have a producer thread each: a patch is requested as soon as its buffer is
+    // free (one unit ahead of the MMAs), whatever the state of the weight ring.
     if (lane == 0) {
-      const uint32_t bfull0 = CG == 2 ? ptx::mapa(bfull_bar(0), 0) : bfull_bar(0);  // completions count on the leader
-      const uint32_t pfull0 = CG == 2 ? ptx::mapa(pfull_bar(0), 0) : pfull_bar(0);
-      const int b_row0 = (int)cta_rank * Cfg::B_ROWS;
-      uint32_t b_dst = b_base, bf = bfull0, bf_l = bfull_bar(0), be = bempty_bar(0);
-      const uint32_t bf_end = bfull_bar(B_STAGES);
-      uint32_t b_phase = 0;
+      const uint32_t pfull0 = CG == 2 ? ptx::mapa(pfull_bar(0), 0) : pfull_bar(0);  // completions count on the leader
       int pb = 0;
       uint32_t p_phase = 0;
       pdl_wait();
@@ -184,10 +189,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         int hp, dst_rows, row0;
         placement(v0l, hp, dst_rows, row0);
         const uint32_t dst_off = (uint32_t)(dst_rows * 128);
-        const int b_row = n_tile * BLOCK_N + b_row0;
-        int k0 = 0;
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
-          // ---- the patch of this 64-channel block ----
           ptx::mbar_wait(pempty_bar(pb), p_phase ^ 1u);
           if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(pfull_bar(pb), CG * p.patch_bytes);
           else ptx::mbar_arrive_cluster(pfull0 + 8u * pb);
@@ -195,8 +197,24 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           ptx::tma_load_4d<CG>(patch_base + pb * p.patch_stride + dst_off, &tmap_x, pfull0 + 8u * pb, cb * PT_BLOCK_K, -1,
                                hp - 1, img);
           if (++pb == 2) { pb = 0; p_phase ^= 1u; }
-          // ---- its nine weight slabs ----
-          int k = k0;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == Cfg::WEIGHT_WARP) {
+    // ===================== TMA producer: weights (one thread) =====================
+    // nine 64-channel tap slabs per channel block; constants, so no wait for the previous kernel
+    if (lane == 0) {
+      const uint32_t bfull0 = CG == 2 ? ptx::mapa(bfull_bar(0), 0) : bfull_bar(0);
+      const int b_row0 = (int)cta_rank * Cfg::B_ROWS;
+      uint32_t b_dst = b_base, bf = bfull0, bf_l = bfull_bar(0), be = bempty_bar(0);
+      const uint32_t bf_end = bfull_bar(B_STAGES);
+      uint32_t b_phase = 0;
+      for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
+        const int n_tile = tile - pt_div(tile, p.div_ntiles) * p.num_n_tiles;
+        const int b_row = n_tile * BLOCK_N + b_row0;
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          int k = cb * PT_BLOCK_K;
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(be, b_phase ^ 1u);
             if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(bf_l, CG * Cfg::B_BYTES);
@@ -206,7 +224,6 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             b_dst += Cfg::B_BYTES; bf += 8; bf_l += 8; be += 8;
             if (bf_l == bf_end) { b_dst = b_base; bf = bfull0; bf_l = bfull_bar(0); be = bempty_bar(0); b_phase ^= 1u; }
           }
-          k0 += PT_BLOCK_K;
         }
       }
     }
@@ -265,11 +282,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2 .. 2 + 4 * EW - 1) =====================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    const int e_tid = (warp - 2) * 32 + lane;  // 0..255
+    const int e_tid = (warp - 2) * 32 + lane;  // 0 .. EPI_THREADS - 1
     const int c_first = half * Cfg::COLS;
     constexpr int NBLK = Cfg::COLS / 64;       // 64-column blocks of this warp
     const uint32_t tempty0 = (CG == 2 && cta_rank != 0) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
@@ -313,7 +330,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                                      : make_uint4(0u, 0u, 0u, 0u);
       }
       if (e_tid < BLOCK_N) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * e_tid), "f"(bias_v) : "memory");
-      ptx::named_bar_sync(1, 256);
+      ptx::named_bar_sync(1, Cfg::EPI_THREADS);
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
 #pragma unroll
@@ -499,7 +516,7 @@ static int launch_patch(const y3_conv_desc* d, const void* x, const void* w, con
   const int grid = CG * (p.num_tiles < slots ? p.num_tiles : slots);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(PT_THREADS);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = pl.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
