@@ -214,7 +214,8 @@ def main_ours(args, rank, local_rank, world):
     key = ("det_u8", PROB_THRESH, IOU_THRESH)
     # the steps alternate between `plans` independent execution plans, each on its own stream
     P = max(1, args.plans)
-    plans = [eng] if P == 1 else [net.engine(B, SIZE, SIZE, slot=200 + k, concurrent=True) for k in range(P)]
+    plans = [eng] if P == 1 else [net.engine(B, SIZE, SIZE, slot=200 + k, concurrent=os.environ.get('Y3_PLANS_PDL', '0') != '1')
+                                    for k in range(P)]
     streams = [torch.cuda.Stream(device=dev) for _ in plans]
     for pl in plans:
         pl.orig_hw.copy_(torch.tensor([[SIZE, SIZE]] * B, dtype=torch.int32))
