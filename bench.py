@@ -256,14 +256,16 @@ def main_ours(args, rank, local_rank, world):
     e1.record()
     barrier()
     dt = e0.elapsed_time(e1) * 1e-3
+    if rank == 0:  # clocks are sampled during the device-timed region only: 50 Hz nvidia-smi polling perturbs host-paced code
+        clocks = sampler.stop()
     last = plans[(args.steps - 1) % P]
     kept_last = int(last.det_counts.sum().item())
     cands_last = int(last.counts.sum().item())
 
     # ---- e2e through the public API, host buffers ------------------------------------------------
     host_lists = [list(b) for b in host_batches]
-    e2e_steps = max(3, min(args.steps, 40))
-    for i in range(5):  # every one of the four rotating batches once: pinned result buffers reach steady state
+    e2e_steps = max(3, min(args.steps, 100))  # ~0.7 s of host-paced calls: single hiccups (VM scheduling) average out
+    for i in range(12):  # the four rotating batches three times: the pinned-memory cache reaches its steady state
         yolov3_b200.inference(net, host_lists[i % 4], device=str(dev), prob_thresh=PROB_THRESH,
                               nms_iou_thresh=IOU_THRESH, resize=False)
         if world > 1:  # NCCL sets its point-to-point channels up on the first gather: not part of a step
@@ -281,8 +283,6 @@ def main_ours(args, rank, local_rank, world):
         d2h = sum(len(r[1]) for r in res) * 32 + B * 4 + B * eng.num_classes * 4
     barrier()
     dt_e2e = time.perf_counter() - t0
-    if rank == 0:
-        clocks = sampler.stop()
 
     # ---- max over ranks ------------------------------------------------------------------------------
     times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)

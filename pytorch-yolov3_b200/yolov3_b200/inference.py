@@ -201,7 +201,11 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
                 continue
             # results live in fresh pinned arrays (torch's caching host allocator recycles them once
             # the caller drops the result), so the device writes the final dtypes and nothing is re-copied
-            tlbr, prob, cls = _pinned((total, 4), torch.int64), _pinned((total,), torch.float32), _pinned((total,), torch.int64)
+            # (capacities are rounded up to 16 Ki detections, so the allocator sees a handful of distinct sizes and
+            # stops calling cudaHostAlloc after the first few batches)
+            cap = (total + 16383) // 16384 * 16384
+            tlbr, prob, cls = (_pinned((cap, 4), torch.int64)[:total], _pinned((cap,), torch.float32)[:total],
+                               _pinned((cap,), torch.int64)[:total])
             with torch.cuda.stream(st):
                 dstbuf.numpy()[...] = dst_off + base
                 eng.dst_off.copy_(dstbuf, non_blocking=True)
