@@ -277,3 +277,13 @@ def test_reciprocal_division_is_exact_over_the_kernels_ranges():
         for x in xs:
             if x * d < (1 << 48):
                 assert fast_div(x, d) == x // d, (x, d)
+
+
+def test_set_pdl_returns_the_previous_setting():
+    """y3_set_pdl is host state only (no CUDA call): usable on a CPU box, returns what was set before."""
+    first = _lib.set_pdl(False)
+    try:
+        assert _lib.set_pdl(True) is False
+        assert _lib.set_pdl(True) is True
+    finally:
+        _lib.set_pdl(first)
