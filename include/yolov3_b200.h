@@ -10,7 +10,8 @@
  * Conventions
  *   - plain C types only; device buffers are raw pointers owned by the caller
  *     (PyTorch allocates them); the library never
- *     allocates or frees device memory and keeps no mutable global state;
+ *     allocates or frees device memory; its only mutable state is per calling
+ *     thread (error message, launch counter, the y3_set_pdl choice);
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as
  *     void*), does no device synchronisation and is CUDA-graph capturable;
  *   - return 0 on success, a Y3_E* code otherwise; y3_last_error() returns a
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 5
+#define Y3_ABI_VERSION 6
 
 enum {
   Y3_OK = 0,
@@ -55,8 +56,9 @@ void y3_reset_launch_count(void);
  * tail).  on = 0 launches plain kernels instead: the better choice when several independent plans
  * run on different streams at once, because a dependent CTA parked in griddepcontrol.wait holds an
  * SM another plan's kernel could use.  Applies to subsequent launches (a captured CUDA graph keeps
- * what was set at capture time).  Process-wide; returns the previous setting.  Default: on
- * (off when the environment has Y3_NO_PDL=1). */
+ * what was set at capture time).  Per calling thread (threads that build plans concurrently do
+ * not see each other's choice); returns the previous setting.  Default: on (off when the
+ * environment has Y3_NO_PDL=1). */
 int y3_set_pdl(int on);
 
 /* ---- a12: host-side staging of the image batch ---------------------------------------- */
@@ -222,13 +224,28 @@ typedef struct y3_cand {
   int32_t pad_;
 } y3_cand;
 
+/*
+ * The two thresholds of `inference` (prob_thresh, nms_iou_thresh;
+ * yolov3/inference.py:287) as a DEVICE-resident record.  Entry points that
+ * take thresholds by value also take `const y3_thresholds* dev_thresholds`
+ * (nullable): when non-NULL the kernels read the thresholds from it at RUN
+ * time and ignore the by-value arguments, so one captured CUDA graph serves
+ * every threshold setting (the caller updates the 16-byte record with a
+ * stream-ordered copy before replaying the graph).
+ */
+typedef struct y3_thresholds {
+  float prob_thresh;        /* keep prob >= prob_thresh                   */
+  float reserved_;
+  double iou_thresh;        /* suppress iou > iou_thresh                  */
+} y3_thresholds;
+
 /* Fused decode + threshold + compaction.  orig_hw: int32 [N,2] (H,W) on the
  * device.  cands: [N,cap]; counts: int32 [N] (caller zeroes before the first
  * head; heads accumulate).  Candidates beyond cap are dropped and counted. */
 int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits,
-                         float prob_thresh, const int32_t* orig_hw,
-                         y3_cand* cands, int32_t* counts, int32_t cap,
-                         void* stream);
+                         float prob_thresh, const y3_thresholds* dev_thresholds,
+                         const int32_t* orig_hw, y3_cand* cands,
+                         int32_t* counts, int32_t cap, void* stream);
 
 /*
  * YOLO head convolution with the decode fused into its epilogue: the 1x1 convolution feeding a
@@ -240,7 +257,8 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits,
  */
 int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w,
                         const float* bias, const y3_head_desc* head,
-                        float prob_thresh, const int32_t* orig_hw, y3_cand* cands,
+                        float prob_thresh, const y3_thresholds* dev_thresholds,
+                        const int32_t* orig_hw, y3_cand* cands,
                         int32_t* counts, int32_t cap, void* stream);
 
 /* ---- a15/a16: non-max suppression ------------------------------------------ */
@@ -267,10 +285,20 @@ int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w,
  */
 size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes);
 int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap,
-           int32_t num_classes, double iou_thresh, int32_t per_class,
+           int32_t num_classes, double iou_thresh,
+           const y3_thresholds* dev_thresholds, int32_t per_class,
            y3_cand* sorted, uint8_t* keep, int32_t* class_first_box,
            int32_t* class_start, int32_t* class_kept,
            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Destinations for y3_emit_detections with class groups in ASCENDING class
+ * order (what set(class_idx) yields whenever an image holds >= 19 distinct
+ * classes < 128; the host re-orders the few images where it does not):
+ * exclusive scan of class_kept [N,num_segments] in (image, segment) order ->
+ * dst_off [N,num_segments]; det_counts [N] = detections kept per image;
+ * det_counts[N] (one extra entry) = total.  n*num_segments <= 2^20. */
+int y3_plan_destinations(const int32_t* class_kept, int32_t n, int32_t num_segments,
+                         int32_t* dst_off, int32_t* det_counts, void* stream);
 
 /* a17: the arrays `inference` returns (yolov3/inference.py:360-366), in their
  * final dtypes and order, built on the device.  For every (image, segment)
@@ -292,6 +320,13 @@ int y3_compact_kept(const y3_cand* sorted, const uint8_t* keep,
                     const int32_t* counts, int32_t n, int32_t cap,
                     y3_cand* dets, int32_t* det_counts, int32_t flat,
                     void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------ */
+/* With Y3_CONV_TRACE=1 in the environment, CTA 0 of every convolution launch
+ * records clock64() stamps of its pipeline roles; this copies the first n
+ * (<= 96) words of the last traced launch to the host (synchronises the
+ * device; tools/conv_trace.py).  Not used by the hot path. */
+int y3_debug_conv_trace(unsigned long long* out, int n);
 
 #ifdef __cplusplus
 }

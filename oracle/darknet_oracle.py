@@ -207,11 +207,11 @@ def yolo_decode(x, anchors):
     C = P // A - 5
     x = x.reshape(B, A, C + 5, h, w)
     box = x[:, :, 0:4].clone()
-    col = torch.linspace(0, w - 1, w).repeat(h, 1)
-    row = torch.linspace(0, h - 1, h).repeat(w, 1).t().contiguous()
+    col = torch.linspace(0, w - 1, w).repeat(h, 1).to(x.device)  # the reference moves them with .to(device) (:83-84)
+    row = torch.linspace(0, h - 1, h).repeat(w, 1).t().contiguous().to(x.device)
     box[:, :, 0].sigmoid_().add_(col).div_(w)
     box[:, :, 1].sigmoid_().add_(row).div_(h)
-    anc = torch.tensor(anchors)  # ints in the cfg -> int64 tensor, as in the reference (:91-97)
+    anc = torch.tensor(anchors).to(x.device)  # ints in the cfg -> int64 tensor, as in the reference (:91-97)
     box[:, :, 2].exp_().mul_(anc[:, 0].reshape(1, A, 1, 1))
     box[:, :, 3].exp_().mul_(anc[:, 1].reshape(1, A, 1, 1))
     obj = x[:, :, 4:5].clone().sigmoid()
@@ -255,7 +255,7 @@ def forward(x, blocks, net_info, params, capture=None):
         if capture is not None:
             capture[i] = x
     bbox = torch.cat(boxes, dim=1)
-    bbox[:, :, 2:4] = bbox[:, :, 2:4] / torch.tensor([net_info["width"], net_info["height"]])
+    bbox[:, :, 2:4] = bbox[:, :, 2:4] / torch.tensor([net_info["width"], net_info["height"]]).to(bbox.device)
     return {"bbox_xywh": bbox, "class_prob": torch.cat(probs, dim=1), "class_idx": torch.cat(idxs, dim=1)}
 
 

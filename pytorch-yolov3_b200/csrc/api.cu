@@ -24,7 +24,7 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
-static int g_pdl = -1;  // -1: not decided yet (environment), else y3_set_pdl's value
+static thread_local int g_pdl = -1;  // per thread; -1: not decided yet (environment), else y3_set_pdl's value
 
 bool pdl_enabled() {
   if (g_pdl < 0) {

@@ -59,6 +59,7 @@ struct ConvKernelParams {
   float anchor_w[3], anchor_h[3];
   float train_w, train_h;
   float prob_thresh;
+  const y3_thresholds* dyn;  // non-null: thresholds read from device memory at run time
   int box_offset;
   const int* orig_hw;
   uint4* cands;   // y3_cand records, [N][cap]
@@ -124,7 +125,8 @@ __device__ __forceinline__ void emit_cand(const ConvKernelParams& p, int a, bool
                                           const float (&t)[5], float sum, int cls, int lane) {
   // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)  (darknet.py:104-108)
   const float prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(t[4]));
-  const bool pass = valid && prob >= p.prob_thresh;  // inference.py:342
+  const float thresh = p.dyn ? __ldg(&p.dyn->prob_thresh) : p.prob_thresh;
+  const bool pass = valid && prob >= thresh;  // inference.py:342
   uint32_t mask = __ballot_sync(0xffffffffu, pass);
   while (mask) {
     const int leader = __ffs(mask) - 1;
@@ -777,6 +779,7 @@ static int encode_im2col(CUtensorMap* map, const y3_conv_desc* d, const void* x,
 struct DecodeArgs {
   const y3_head_desc* head;
   float prob_thresh;
+  const y3_thresholds* dyn;
   const int* orig_hw;
   void* cands;
   int* counts;
@@ -817,12 +820,13 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
     if (trace < 0) { const char* e = getenv("Y3_CONV_TRACE"); trace = (e && e[0] == '1') ? 1 : 0; }
     p.trace = trace;
   }
-  p.train_w = p.train_h = 1.f; p.prob_thresh = 0.f; p.box_offset = 0;
+  p.train_w = p.train_h = 1.f; p.prob_thresh = 0.f; p.dyn = nullptr; p.box_offset = 0;
   for (int a = 0; a < 3; ++a) p.anchor_w[a] = p.anchor_h[a] = 0.f;
   if (DECODE) {
     for (int a = 0; a < 3; ++a) { p.anchor_w[a] = dec->head->anchor_w[a]; p.anchor_h[a] = dec->head->anchor_h[a]; }
     p.train_w = dec->head->train_w; p.train_h = dec->head->train_h;
     p.prob_thresh = dec->prob_thresh;
+    p.dyn = dec->dyn;
     p.box_offset = dec->head->box_offset;
     p.orig_hw = dec->orig_hw;
     p.cands = reinterpret_cast<uint4*>(dec->cands);
@@ -953,7 +957,7 @@ static int conv2d_impl(const y3_conv_desc* d, const void* x, const void* w, cons
 
 }  // namespace y3
 
-// Diagnostics, not part of the ABI in include/: copy the trace of the last traced launch to the host.
+// Diagnostics (declared at the end of include/yolov3_b200.h): copy the trace of the last traced launch to the host.
 extern "C" int y3_debug_conv_trace(unsigned long long* out, int n) {
   using namespace y3;
   Y3_CHECK_ARG(out && n > 0 && n <= 96, "debug_conv_trace: n=%d", n);
@@ -963,7 +967,8 @@ extern "C" int y3_debug_conv_trace(unsigned long long* out, int n) {
 }
 
 extern "C" int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
-                                   const y3_head_desc* head, float prob_thresh, const int32_t* orig_hw,
+                                   const y3_head_desc* head, float prob_thresh,
+                                   const y3_thresholds* dev_thresholds, const int32_t* orig_hw,
                                    y3_cand* cands, int32_t* counts, int32_t cap, void* stream) {
   using namespace y3;
   Y3_CHECK_ARG(d && x && w && bias && head && orig_hw && cands && counts && cap > 0, "conv2d_yolo_head: null argument");
@@ -979,7 +984,7 @@ extern "C" int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const v
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(cands) & 15) == 0,
                "conv2d_yolo_head: pointers must be 16-byte aligned");
-  DecodeArgs dec = {head, prob_thresh, orig_hw, cands, counts, cap};
+  DecodeArgs dec = {head, prob_thresh, dev_thresholds, orig_hw, cands, counts, cap};
   return launch_conv<256, 64, false, 1, true>(d, x, w, bias, nullptr, const_cast<float*>(bias) /*unused*/,
                                               reinterpret_cast<cudaStream_t>(stream), 0, &dec);
 }

@@ -112,9 +112,10 @@ static constexpr int DEC_CACHED = 11;  // fields cached per lane: 8 * 11 = 88 >=
 
 __global__ void __launch_bounds__(256)
 decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
-                    const int* __restrict__ orig_hw, y3_cand* __restrict__ cands,
-                    int* __restrict__ counts, int cap) {
+                    const y3_thresholds* __restrict__ dyn, const int* __restrict__ orig_hw,
+                    y3_cand* __restrict__ cands, int* __restrict__ counts, int cap) {
   pdl_enter();
+  if (dyn) prob_thresh = dyn->prob_thresh;  // device-resident thresholds: one graph, any setting
   __shared__ uint4 s_rec[CAND_BOXES][2];
   __shared__ int s_count, s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,15 +250,17 @@ int y3_yolo_decode_dense(const y3_head_desc* d, const float* logits, float* bbox
   return Y3_OK;
 }
 
-int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits, float prob_thresh, const int32_t* orig_hw,
-                         y3_cand* cands, int32_t* counts, int32_t cap, void* stream) {
+int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits, float prob_thresh,
+                         const y3_thresholds* dev_thresholds, const int32_t* orig_hw, y3_cand* cands,
+                         int32_t* counts, int32_t cap, void* stream) {
   int rc = check_head(d, logits);
   if (rc != Y3_OK) return rc;
   Y3_CHECK_ARG(orig_hw && cands && counts && cap > 0, "decode_cands: bad output arguments");
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(cands) & 15) == 0, "decode_cands: cands must be 16-byte aligned");
   const int per_img = d->num_anchors * d->g_h * d->g_w;
   const dim3 grid((per_img + CAND_BOXES - 1) / CAND_BOXES, d->n);
-  Y3_CUDA_OK(launch_kernel(decode_cands_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, *d, logits, prob_thresh, orig_hw, cands, counts, cap));
+  Y3_CUDA_OK(launch_kernel(decode_cands_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, *d, logits, prob_thresh,
+                           dev_thresholds, orig_hw, cands, counts, cap));
   Y3_LAUNCH_OK("decode_cands_kernel");
   return Y3_OK;
 }

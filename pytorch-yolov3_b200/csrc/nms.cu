@@ -115,9 +115,11 @@ static constexpr int BITMASK_WORDS = BITMASK_MAX / 32;
 
 __global__ void __launch_bounds__(1024)
 nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
-                   int cap, int C, double thr, y3_cand* __restrict__ sorted,
-                   uint8_t* __restrict__ keep, int* __restrict__ class_kept, int min_n) {
+                   int cap, int C, double thr, const y3_thresholds* __restrict__ dyn,
+                   y3_cand* __restrict__ sorted, uint8_t* __restrict__ keep, int* __restrict__ class_kept,
+                   int min_n) {
   pdl_enter();
+  if (dyn) thr = dyn->iou_thresh;  // device-resident thresholds: one graph, any setting
   __shared__ int4 sbox[BITMASK_MAX];
   __shared__ float skey_p[BITMASK_MAX];
   __shared__ int skey_b[BITMASK_MAX];
@@ -326,9 +328,10 @@ __device__ __forceinline__ float fast_area(int x1, int y1, int x2, int y2) {
 template <int MAXN>
 __global__ void __launch_bounds__(MAXN)
 nms_bitmask_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off, int cap, int C,
-                   double thr, y3_cand* __restrict__ sorted, uint8_t* __restrict__ keep,
-                   int* __restrict__ class_kept, int min_n) {
+                   double thr, const y3_thresholds* __restrict__ dyn, y3_cand* __restrict__ sorted,
+                   uint8_t* __restrict__ keep, int* __restrict__ class_kept, int min_n) {
   pdl_enter();
+  if (dyn) thr = dyn->iou_thresh;
   constexpr int WORDS = MAXN / 32;
   __shared__ float4 sboxf[MAXN];
   __shared__ float sarea[MAXN];
@@ -499,6 +502,48 @@ emit_detections_kernel(const y3_cand* __restrict__ sorted, const uint8_t* __rest
   }
 }
 
+// Destinations of the (image, class) groups for emit_detections_kernel with classes ascending inside an
+// image: exclusive scan of class_kept in (image, class) order by ONE CTA (n*C <= 2^20 values: each thread
+// sums a contiguous run, the run totals are scanned through shared memory), per-image totals on the side.
+__global__ void __launch_bounds__(1024)
+plan_destinations_kernel(const int* __restrict__ class_kept, int n_images, int C, int* __restrict__ dst_off,
+                         int* __restrict__ det_counts) {
+  pdl_enter();
+  __shared__ int warp_tot[32];
+  const int total = n_images * C;
+  const int per = (total + blockDim.x - 1) / blockDim.x;
+  const int lo = min(total, (int)threadIdx.x * per), hi = min(total, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += class_kept[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_tot[lane] = w;  // inclusive totals of warps 0..lane
+  }
+  __syncthreads();
+  int run = incl - sum + (warp ? warp_tot[warp - 1] : 0);
+  for (int i = lo; i < hi; ++i) { dst_off[i] = run; run += class_kept[i]; }
+  if (threadIdx.x == 0) det_counts[n_images] = warp_tot[(blockDim.x >> 5) - 1];
+  for (int img = threadIdx.x; img < n_images; img += blockDim.x) {
+    int k = 0;
+    for (int c = 0; c < C; ++c) k += class_kept[img * C + c];
+    det_counts[img] = k;
+  }
+}
+
 // Ordered compaction of kept records per image; dets are written image after image into one
 // flat array, det_offsets[img] .. det_offsets[img+1] (exclusive scan done by nms_offsets_kernel).
 __global__ void __launch_bounds__(1024)
@@ -574,7 +619,8 @@ size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes) {
 }
 
 int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, int32_t num_classes,
-           double iou_thresh, int32_t per_class, y3_cand* sorted, uint8_t* keep, int32_t* class_first_box,
+           double iou_thresh, const y3_thresholds* dev_thresholds, int32_t per_class, y3_cand* sorted,
+           uint8_t* keep, int32_t* class_first_box,
            int32_t* class_start, int32_t* class_kept, void* workspace, size_t workspace_bytes, void* stream) {
   Y3_CHECK_ARG(cands && counts && sorted && keep && workspace, "nms: null argument");
   Y3_CHECK_ARG(n > 0 && cap > 0, "nms: bad n=%d cap=%d", n, cap);
@@ -599,18 +645,29 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
   // segments of <= FAST_SEG_MAX boxes: three size classes of the fp32 bit-matrix kernel; the rest (if any):
   // nms_segment_kernel.  Each launch covers every segment and returns at once for foreign sizes.
   Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<128>, dim3(C, n), dim3(128), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           sorted, keep, class_kept, 0));
+                           dev_thresholds, sorted, keep, class_kept, 0));
   Y3_LAUNCH_OK("nms_bitmask_kernel<128>");
   Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<256>, dim3(C, n), dim3(256), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           sorted, keep, class_kept, 128));
+                           dev_thresholds, sorted, keep, class_kept, 128));
   Y3_LAUNCH_OK("nms_bitmask_kernel<256>");
   Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<512>, dim3(C, n), dim3(512), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           sorted, keep, class_kept, 256));
+                           dev_thresholds, sorted, keep, class_kept, 256));
   Y3_LAUNCH_OK("nms_bitmask_kernel<512>");
   const int threads = per_class ? 256 : 1024;  // one huge segment per image: more threads per CTA
-  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(dim3(C, n)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh, sorted, keep,
-                           class_kept, FAST_SEG_MAX + 1));
+  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(dim3(C, n)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh, dev_thresholds,
+                           sorted, keep, class_kept, FAST_SEG_MAX + 1));
   Y3_LAUNCH_OK("nms_segment_kernel");
+  return Y3_OK;
+}
+
+int y3_plan_destinations(const int32_t* class_kept, int32_t n, int32_t num_segments, int32_t* dst_off,
+                         int32_t* det_counts, void* stream) {
+  Y3_CHECK_ARG(class_kept && dst_off && det_counts, "plan_destinations: null argument");
+  Y3_CHECK_ARG(n > 0 && num_segments > 0 && (long long)n * num_segments <= (1ll << 20),
+               "plan_destinations: n=%d x segments=%d out of range", n, num_segments);
+  Y3_CUDA_OK(launch_kernel(plan_destinations_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, class_kept, n,
+                           num_segments, dst_off, det_counts));
+  Y3_LAUNCH_OK("plan_destinations_kernel");
   return Y3_OK;
 }
 

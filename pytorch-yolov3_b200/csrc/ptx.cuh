@@ -55,13 +55,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 // Blocking wait with a watchdog: a protocol bug traps (-> CUDA error on the
-// host) instead of hanging the GPU box.  ~2 s at 2 GHz before giving up.
+// host) instead of hanging the GPU box.  ~8 s at 2 GHz before giving up (far beyond any
+// legitimate stall: a whole 64-image step takes 4 ms).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   uint32_t it = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++it) & 0x3FFu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    if (((++it) & 0x3FFu) == 0 && clock64() - t0 > 16000000000ll) __trap();
   }
 }
 

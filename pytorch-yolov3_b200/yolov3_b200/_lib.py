@@ -22,10 +22,11 @@ EXPORTS = (
     "y3_abi_version", "y3_last_error", "y3_check_device", "y3_launch_count", "y3_reset_launch_count", "y3_set_pdl",
     "y3_stage_images", "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
-    "y3_nms_workspace_bytes", "y3_nms", "y3_compact_kept", "y3_emit_detections",
+    "y3_nms_workspace_bytes", "y3_nms", "y3_plan_destinations", "y3_compact_kept", "y3_emit_detections",
+    "y3_debug_conv_trace",
 )
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class ConvDesc(ctypes.Structure):
@@ -45,6 +46,11 @@ class HeadDesc(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "n", "g_h", "g_w", "num_anchors", "num_classes", "ld", "box_offset", "boxes_per_image")] + [
         ("anchor_w", c_float * 8), ("anchor_h", c_float * 8), ("train_w", c_float), ("train_h", c_float)]
+
+
+class Thresholds(ctypes.Structure):
+    """``y3_thresholds`` (16 bytes; the device-resident copy is what the kernels read)."""
+    _fields_ = [("prob_thresh", c_float), ("reserved_", c_float), ("iou_thresh", c_double)]
 
 
 # numpy / torch view of ``y3_cand`` (32 bytes)
@@ -71,7 +77,7 @@ def lib():
     L.y3_stage_images.argtypes = [c_void_p, POINTER(c_void_p), c_int32, c_int64, c_int32]
     L.y3_conv2d.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.y3_conv2d_yolo_head.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, POINTER(HeadDesc), c_float,
-                                      c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     L.y3_conv_chain_stem_u8.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
     L.y3_conv_chain_res64.argtypes = [POINTER(ChainDesc)] + [c_void_p] * 7
     L.y3_maxpool.argtypes = [c_void_p, c_void_p] + [c_int32] * 8 + [c_void_p]
@@ -84,12 +90,14 @@ def lib():
     L.y3_im2col3x3_nchw_f32.argtypes = [c_void_p] * 2 + [c_int32] * 5 + [c_void_p]
     L.y3_im2col3x3_bgr_u8.argtypes = [c_void_p] * 2 + [c_int32] * 4 + [c_void_p]
     L.y3_yolo_decode_dense.argtypes = [POINTER(HeadDesc)] + [c_void_p] * 5
-    L.y3_yolo_decode_cands.argtypes = [POINTER(HeadDesc), c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+    L.y3_yolo_decode_cands.argtypes = [POINTER(HeadDesc), c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p]
     L.y3_nms_workspace_bytes.argtypes = [c_int32] * 3
     L.y3_nms_workspace_bytes.restype = c_size_t
-    L.y3_nms.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_int32, c_void_p, c_void_p,
+    L.y3_nms.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double, c_void_p, c_int32, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.y3_plan_destinations.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    L.y3_debug_conv_trace.argtypes = [c_void_p, ctypes.c_int]
     L.y3_emit_detections.argtypes = [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 4
     L.y3_compact_kept.argtypes = [c_void_p] * 3 + [c_int32] * 2 + [c_void_p] * 2 + [c_int32, c_void_p]
     if L.y3_abi_version() != ABI_VERSION:
@@ -164,11 +172,15 @@ def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, 
     _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
 
 
-def conv2d_yolo_head(x_ptr, w, bias, head, prob_thresh, orig_hw, cands, counts, cap, *, n, h, w_in, cin, ld_x):
-    """1x1 YOLO head convolution with decode + threshold + candidate append fused into its epilogue."""
+def conv2d_yolo_head(x_ptr, w, bias, head, prob_thresh, orig_hw, cands, counts, cap, *, n, h, w_in, cin, ld_x,
+                     dev_thresholds=None):
+    """1x1 YOLO head convolution with decode + threshold + candidate append fused into its epilogue.
+    ``dev_thresholds``: device tensor holding a ``y3_thresholds`` record read at run time (overrides
+    ``prob_thresh``)."""
     d = ConvDesc(n, h, w_in, cin, 256, 1, 1, 0, ld_x, 256, 0, 0, 0, 0, 0)
     _check(lib().y3_conv2d_yolo_head(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), ctypes.byref(head),
-                                     float(prob_thresh), _ptr(orig_hw), _ptr(cands), _ptr(counts), cap, _stream()))
+                                     float(prob_thresh), _ptr(dev_thresholds), _ptr(orig_hw), _ptr(cands),
+                                     _ptr(counts), cap, _stream()))
 
 
 def conv_chain_stem_u8(img, w1, b1, w2, b2, y_ptr, *, ld_y, leaky1=True, leaky2=True):
@@ -246,9 +258,9 @@ def yolo_decode_dense(desc, logits, bbox_xywh, class_prob, class_idx):
                                       _ptr(class_idx), _stream()))
 
 
-def yolo_decode_cands(desc, logits, prob_thresh, orig_hw, cands, counts, cap):
-    _check(lib().y3_yolo_decode_cands(ctypes.byref(desc), _ptr(logits), float(prob_thresh), _ptr(orig_hw),
-                                      _ptr(cands), _ptr(counts), cap, _stream()))
+def yolo_decode_cands(desc, logits, prob_thresh, orig_hw, cands, counts, cap, dev_thresholds=None):
+    _check(lib().y3_yolo_decode_cands(ctypes.byref(desc), _ptr(logits), float(prob_thresh), _ptr(dev_thresholds),
+                                      _ptr(orig_hw), _ptr(cands), _ptr(counts), cap, _stream()))
 
 
 def nms_workspace_bytes(n, cap, num_classes):
@@ -256,10 +268,16 @@ def nms_workspace_bytes(n, cap, num_classes):
 
 
 def nms(cands, counts, n, cap, num_classes, iou_thresh, per_class, sorted_out, keep, class_first_box, workspace,
-        class_start=None, class_kept=None):
-    _check(lib().y3_nms(_ptr(cands), _ptr(counts), n, cap, num_classes, float(iou_thresh), int(per_class),
+        class_start=None, class_kept=None, dev_thresholds=None):
+    _check(lib().y3_nms(_ptr(cands), _ptr(counts), n, cap, num_classes, float(iou_thresh), _ptr(dev_thresholds),
+                        int(per_class),
                         _ptr(sorted_out), _ptr(keep), _ptr(class_first_box), _ptr(class_start), _ptr(class_kept),
                         _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()))
+
+
+def plan_destinations(class_kept, n, num_segments, dst_off, det_counts):
+    """Ascending-class destinations + per-image totals (``det_counts`` has n + 1 entries: last = total)."""
+    _check(lib().y3_plan_destinations(_ptr(class_kept), n, num_segments, _ptr(dst_off), _ptr(det_counts), _stream()))
 
 
 def emit_detections(sorted_in, keep, class_start, dst_off, n, cap, num_segments, tlbr, prob, cls):

@@ -11,11 +11,19 @@ the tcgen05 convolution epilogues, the whole forward replayed as one CUDA graph.
 
 There is no CPU path: ``forward`` raises unless it can run on an sm_100 CUDA device.
 """
+import os
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
 from . import _lib
 from .engine import Engine
+
+# compiled plans kept per network: least-recently-used geometries (batch, height, width) beyond this
+# many are dropped together with their buffers, graphs and staging memory (a video loop with a ragged
+# last batch or a resolution sweep must not grow without bound)
+MAX_GEOMETRIES = int(os.environ.get("Y3_MAX_GEOMETRIES", "6"))
 
 
 class DummyLayer(torch.nn.Module):
@@ -29,16 +37,20 @@ class MaxPool2d(torch.nn.MaxPool2d):
     float tensors like the reference module and run the CUDA kernel."""
 
     def forward(self, input_):
+        """Deviation from the reference module (documented in INTEGRATION.md): the kernel works on the
+        network's activation format, NHWC bf16 with channels in multiples of 8, so a stand-alone call
+        rounds its input to bf16 (max of bf16 values is exact) and zero-pads the channel axis up to a
+        multiple of 8 internally (the padding never reaches the result)."""
         dev = _lib.require_device(input_.device)
         n, c, h, w = input_.shape
-        if c % 8:
-            raise RuntimeError("MaxPool2d: channel count must be a multiple of 8")
-        x = input_.to(dev).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        cp = (c + 7) // 8 * 8
+        x = torch.zeros(n, h, w, cp, device=dev, dtype=torch.bfloat16)
+        x[..., :c] = input_.to(dev).permute(0, 2, 3, 1)
         k, s = int(self.kernel_size), int(self.stride)
         ho, wo = (h, w) if (k > 1 and s == 1) else ((h - k) // s + 1, (w - k) // s + 1)
-        y = torch.empty(n, ho, wo, c, device=dev, dtype=torch.bfloat16)
-        _lib.maxpool(x.data_ptr(), y.data_ptr(), n, h, w, c, c, c, k, s)
-        return y.permute(0, 3, 1, 2).to(input_.dtype)
+        y = torch.empty(n, ho, wo, cp, device=dev, dtype=torch.bfloat16)
+        _lib.maxpool(x.data_ptr(), y.data_ptr(), n, h, w, cp, cp, cp, k, s)
+        return y[..., :c].permute(0, 3, 1, 2).to(input_.dtype)
 
 
 class YOLOLayer(torch.nn.Module):
@@ -180,8 +192,9 @@ class Darknet(torch.nn.Module):
                     self.blocks_to_cache.add(b["layers"][j])
             elif b["type"] == "shortcut":
                 self.blocks_to_cache.update((i - 1, i + b["from"]))
-        self._engines = {}
+        self._geometries = OrderedDict()  # (batch, height, width) -> {"engines": {slot: Engine}, ...}, LRU order
         self._weights_version = 0
+        self._token = None
 
     # -- parameters ------------------------------------------------------------------------
     def load_weights(self, weights_path):
@@ -218,10 +231,49 @@ class Darknet(torch.nn.Module):
         return self
 
     def invalidate(self):
-        """Drop compiled plans (call after editing parameters in place)."""
-        self._engines.clear()
-        self.__dict__.pop("_host_io", None)  # inference()'s staging buffers hold plans too
-        self._weights_version += 1
+        """Drop compiled plans, folded weights and staging buffers.  Called by everything that can change
+        the parameters behind the plans' back: ``load_weights``, ``load_state_dict``, ``.to()/.cuda()/
+        .half()...`` (``_apply``), and by ``engine()`` itself when a parameter's version counter moved
+        (in-place edits under ``torch.no_grad()``).  Writes through ``param.data`` bypass the version
+        counter — call this by hand after such edits."""
+        self.__dict__.setdefault("_geometries", OrderedDict()).clear()
+        self.__dict__.pop("_folded_cache", None)
+        self._weights_version = self.__dict__.get("_weights_version", 0) + 1
+        self._token = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _weights_token(self):
+        """Cheap fingerprint of the parameters / BN statistics: sum of the tensors' version counters
+        plus their identity (a replaced Parameter object changes it)."""
+        tensors = self.__dict__.get("_tracked")
+        if tensors is None or self._token is None:
+            tensors = [t for t in list(self.parameters()) + list(self.buffers())]
+            self.__dict__["_tracked"] = tensors
+        return sum(t._version for t in tensors)
+
+    def check_fresh(self):
+        """Raise / refresh before running: plans must match the live parameters, and the network must
+        be in eval mode — the plans fold BatchNorm's RUNNING statistics into the weights, which is what
+        the reference computes after ``net.eval()`` (its CLI always calls it, yolov3/__main__.py:117);
+        in train mode the reference would normalise with batch statistics instead."""
+        if self.training and any(isinstance(m, torch.nn.BatchNorm2d) for m in self.modules()):
+            raise RuntimeError("yolov3_b200.Darknet runs inference with BatchNorm folded into the weights: call "
+                               "net.eval() first (train-mode batch statistics are not implemented)")
+        tok = self._weights_token()
+        if self._token is None:
+            self._token = tok
+        elif tok != self._token:
+            self.invalidate()
+            self._token = self._weights_token()
 
     # -- execution ------------------------------------------------------------------------------
     def _target_device(self):
@@ -238,12 +290,25 @@ class Darknet(torch.nn.Module):
         ``inference`` pipelines sub-batches through several of them.  ``concurrent`` (honoured when
         the plan is first built) marks a plan that runs next to others on different streams: its
         graphs are captured without programmatic dependent launch (see ``y3_set_pdl``)."""
-        key = (batch, height, width) if slot == 0 else (batch, height, width, slot)
-        eng = self._engines.get(key)
+        geom = self.geometry(batch, height, width)
+        eng = geom["engines"].get(slot)
         if eng is None:
             eng = Engine(self, batch, height, width, self._target_device(), pdl=not concurrent)
-            self._engines[key] = eng
+            geom["engines"][slot] = eng
         return eng
+
+    def geometry(self, batch, height, width):
+        """Per-geometry cache entry (plans by slot + whatever ``inference`` keeps beside them), most
+        recently used last; the least recently used entries beyond ``MAX_GEOMETRIES`` are dropped."""
+        key = (int(batch), int(height), int(width))
+        geom = self._geometries.get(key)
+        if geom is None:
+            geom = self._geometries[key] = {"engines": {}}
+            while len(self._geometries) > max(1, MAX_GEOMETRIES):
+                self._geometries.popitem(last=False)
+        else:
+            self._geometries.move_to_end(key)
+        return geom
 
     def forward(self, x):
         """Full forward + decode (reference: yolov3/darknet.py:351-405).
@@ -256,5 +321,6 @@ class Darknet(torch.nn.Module):
         """
         if x.dim() != 4 or x.shape[1] != self.net_info["channels"]:
             raise RuntimeError(f"expected input [B,{self.net_info['channels']},H,W], got {tuple(x.shape)}")
+        self.check_fresh()
         eng = self.engine(x.shape[0], x.shape[2], x.shape[3])
         return eng.forward_dense(x)

@@ -6,6 +6,8 @@ the only collective is the gather of kept detections after NMS:
 Works with any ``torch.distributed`` backend: NCCL with CUDA tensors on the B200 box, gloo with
 CPU tensors in the host-logic tests.
 """
+from collections import deque
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -81,7 +83,9 @@ def gather_detections(rec, counts, group=None, device=None):
 
 
 def gather_outputs(tlbr, prob, cls, per_image, group=None, dst=0):
-    """Gather the final detection arrays of every rank on rank ``dst`` WITHOUT a host round trip.
+    """Gather the final detection arrays of every rank on GLOBAL rank ``dst`` (a member of ``group``)
+    after a synchronous ``inference()`` call.  (``inference_batches(..., gather=DetectionGather())`` is
+    the pipelined form without host round trips.)
 
     ``tlbr`` int64 [K,4], ``prob`` float32 [K], ``cls`` int64 [K] are this rank's detections, images
     back to back (``Engine.out_tlbr[:K]`` etc. after ``inference()``), ``per_image`` the detections
@@ -91,7 +95,7 @@ def gather_outputs(tlbr, prob, cls, per_image, group=None, dst=0):
     per-image counts int64 numpy [B_total])``; on the other ranks ``(None, counts)``.
     """
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    rank = dist.get_rank()  # global, like ``dst`` (dist.gather's dst is a global rank)
     device = tlbr.device
     cnt = torch.as_tensor(np.asarray(per_image, dtype=np.int64)).to(device)
     meta = torch.tensor([cnt.numel(), int(prob.shape[0])], dtype=torch.int64, device=device)
@@ -123,3 +127,68 @@ def gather_outputs(tlbr, prob, cls, per_image, group=None, dst=0):
         return None, counts
     per_rank = [(parts[0][r][:metas[r, 1]], parts[1][r][:metas[r, 1]], parts[2][r][:metas[r, 1]]) for r in range(world)]
     return per_rank, counts
+
+
+class DetectionGather:
+    """The hot path's only collective, in the form ``inference_batches`` drives without host round
+    trips of its own: per batch ONE small ``all_gather`` of every rank's per-image
+    detection counts, issued on the stream right behind the batch's CUDA graph, and — once the host has
+    read them together with its own counts (it has to wait for those anyway to size its download) — ONE
+    ``gather`` per output array of exactly ``max over ranks`` detections (rounded up to 4096) onto
+    global rank ``dst``.  Every rank derives the same size from the same gathered counts, so no rank
+    waits for another on the host.  Works with NCCL (device tensors) and gloo (CPU tensors, tests).
+
+    After batch k's payload has been queued, ``last`` = ``(per_rank, counts)`` on ``dst`` — ``per_rank[r]``
+    = ``(tlbr int64 [K_r,4], prob float32 [K_r], cls int64 [K_r])`` views of the receive buffers (valid
+    once the stream has caught up; overwritten by this slot's next batch), ``counts`` int64 numpy
+    ``[world, B]`` — and ``(None, counts)`` elsewhere.
+    """
+
+    def __init__(self, group=None, dst=0):
+        self.group, self.dst = group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank()
+        self._queue = deque()
+        self.last = None
+        self.bytes_gathered = 0
+
+    @staticmethod
+    def _host(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+
+    def post_counts(self, eng):
+        """Queue the all-gather of ``eng.det_counts_total`` ([B] per-image counts + total) and its copy
+        to the host, on the current stream."""
+        st = eng.__dict__.setdefault("_gather_state", {})
+        n = eng.det_counts_total.numel()
+        if "counts" not in st:
+            st["counts"] = torch.zeros(self.world * n, dtype=torch.int32, device=eng.det_counts_total.device)
+            st["counts_host"] = self._host((self.world * n,), torch.int32)
+        dist.all_gather_into_tensor(st["counts"], eng.det_counts_total, group=self.group)
+        st["counts_host"].copy_(st["counts"], non_blocking=True)
+        self._queue.append(eng)
+
+    def gather_payload(self, eng, total):
+        """Queue the gather of this batch's detections (call once the copy queued by ``post_counts`` has
+        completed, i.e. after the batch's meta event).  ``total`` = this rank's detections."""
+        assert self._queue.popleft() is eng, "DetectionGather: batches must be finished in submission order"
+        st = eng._gather_state
+        B = eng.det_counts_total.numel() - 1
+        allc = st["counts_host"].numpy().reshape(self.world, B + 1).astype(np.int64)
+        assert int(allc[self.rank if self.group is None else dist.get_rank(self.group), B]) == int(total)
+        cap = eng.out_prob.shape[0]
+        n = min(cap, max(4096, (int(allc[:, B].max()) + 4095) // 4096 * 4096))
+        srcs = (eng.out_tlbr, eng.out_prob, eng.out_cls)
+        if self.rank == self.dst and "recv" not in st:
+            st["recv"] = [torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in srcs]
+        for j, t in enumerate(srcs):
+            bufs = [st["recv"][j][r, :n] for r in range(self.world)] if self.rank == self.dst else None
+            dist.gather(t[:n], bufs, dst=self.dst, group=self.group)
+            self.bytes_gathered += n * t[0].numel() * t.element_size() * (self.world if self.rank == self.dst else 1)
+        counts = allc[:, :B]
+        if self.rank == self.dst:
+            per_rank = [tuple(st["recv"][j][r, :int(allc[r, B])] for j in range(3)) for r in range(self.world)]
+            self.last = (per_rank, counts)
+        else:
+            self.last = (None, counts)
+        return self.last

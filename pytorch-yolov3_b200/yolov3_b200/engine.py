@@ -17,6 +17,7 @@ What it decides once, at build time (reference semantics: yolov3/darknet.py:351-
     compaction) for ``inference``.
 """
 import os
+import struct
 
 import numpy as np
 import torch
@@ -203,15 +204,18 @@ class Engine:
         self.op_names = []  # "stem_unfused" / "stem_fused" = alternative forms of blocks 0-1 (see run_backbone)
         self.op_groups = []
 
-        def emit(name, fn, group=None):
+        self.mem_ops = []  # (name, launch closure, algorithmic HBM bytes) of the memory-bound block kernels
+
+        def emit(name, fn, group=None, hbm_bytes=None):
             ops.append(fn)
             self.op_names.append(name)
             self.op_groups.append(group)
+            if hbm_bytes is not None:
+                self.mem_ops.append((name, fn, hbm_bytes))
 
         use_chain = os.environ.get("Y3_NO_CHAIN", "0") != "1"
         use_fused_decode = os.environ.get("Y3_NO_FUSED_DECODE", "0") != "1"
         self.num_fused_heads = 0
-        self._prob_thresh = 0.0
 
         def conv_geom(j):
             bj = blocks[j]
@@ -305,8 +309,9 @@ class Engine:
                 emit(f"conv{i}", fn, "stem_unfused" if in_stem else ("head_logits" if fuse_head else None))
                 if fuse_head:
                     hfn = (lambda xp=xin.ptr, w=w, bias=bias, hk=len(heads), h=xin.H, wi=xin.W, c=xin.C, lx=xin.ld:
-                           _lib.conv2d_yolo_head(xp, w, bias, self.head_descs[hk][0], self._prob_thresh, self.orig_hw,
-                                                 self.cands, self.counts, self.cap, n=B, h=h, w_in=wi, cin=c, ld_x=lx))
+                           _lib.conv2d_yolo_head(xp, w, bias, self.head_descs[hk][0], 0.0, self.orig_hw,
+                                                 self.cands, self.counts, self.cap, n=B, h=h, w_in=wi, cin=c, ld_x=lx,
+                                                 dev_thresholds=self.thresh))
                     emit(f"headconv{i}", hfn, "head_fused")
                     self.num_fused_heads += 1
                 ho, wo = shape[i][1], shape[i][2]
@@ -356,28 +361,31 @@ class Engine:
                         done.add(j)
                     if len({v.ld for v in vs}) == 1:
                         emit(f"spp{i}", lambda xp=xin.ptr, a=vs[0].ptr, b_=vs[1].ptr, c=vs[2].ptr, h=xin.H, w=xin.W,
-                             C=xin.C, lx=xin.ld, ly=vs[0].ld: _lib.spp3(xp, a, b_, c, B, h, w, C, lx, ly))
+                             C=xin.C, lx=xin.ld, ly=vs[0].ld: _lib.spp3(xp, a, b_, c, B, h, w, C, lx, ly),
+                             hbm_bytes=B * xin.H * xin.W * xin.C * 2 * 4)  # one read, three pooled writes
                     else:
                         for j, v in zip(trio, vs):
                             emit(f"maxpool{j}", lambda xp=xin.ptr, yp=v.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld,
-                                 ly=v.ld, kk=blocks[j]["size"]: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, 1))
+                                 ly=v.ld, kk=blocks[j]["size"]: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, 1),
+                                 hbm_bytes=B * xin.H * xin.W * xin.C * 2 * 2)
                 else:
                     yv = alloc(i)
                     views[i] = yv
                     emit(f"maxpool{i}", lambda xp=xin.ptr, yp=yv.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld, ly=yv.ld,
-                         kk=k, ss=s: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, ss))
+                         kk=k, ss=s: _lib.maxpool(xp, yp, B, h, w, C, lx, ly, kk, ss),
+                         hbm_bytes=B * xin.C * 2 * (xin.H * xin.W + yv.H * yv.W))
             elif t == "upsample":  # not fused: stand-alone kernel
                 xin = views[inputs_of(i)[0]]
                 yv = alloc(i)
                 views[i] = yv
                 emit(f"upsample{i}", lambda xp=xin.ptr, yp=yv.ptr, h=xin.H, w=xin.W, C=xin.C, lx=xin.ld, ly=yv.ld:
-                     _lib.upsample2x(xp, yp, B, h, w, C, lx, ly))
+                     _lib.upsample2x(xp, yp, B, h, w, C, lx, ly), hbm_bytes=B * xin.H * xin.W * xin.C * 2 * 5)
             elif t == "shortcut":  # not fused: stand-alone add
                 a, r = (views[j] for j in inputs_of(i))
                 yv = alloc(i)
                 views[i] = yv
                 emit(f"add{i}", lambda ap=a.ptr, bp=r.ptr, yp=yv.ptr, px=B * a.H * a.W, C=a.C, la=a.ld, lb=r.ld,
-                     ly=yv.ld: _lib.add(ap, bp, yp, px, C, la, lb, ly))
+                     ly=yv.ld: _lib.add(ap, bp, yp, px, C, la, lb, ly), hbm_bytes=B * a.H * a.W * a.C * 2 * 3)
             elif t == "route":
                 if len(b["layers"]) == 1:
                     views[i] = views[root(i)]
@@ -391,7 +399,8 @@ class Engine:
                         if sv.f32 or sv.C % 8 or off % 8:
                             raise NotImplementedError(f"block {i}: cannot concatenate source block {j}")
                         emit(f"copy{i}_{j}", lambda xp=sv.ptr, yp=_p(buf) + off * 2, px=B * sv.H * sv.W,
-                             C=shape[j][0], lx=sv.ld, ly=buf.shape[3]: _lib.copy_channels(xp, yp, px, C, lx, ly))
+                             C=shape[j][0], lx=sv.ld, ly=buf.shape[3]: _lib.copy_channels(xp, yp, px, C, lx, ly),
+                             hbm_bytes=B * sv.H * sv.W * shape[j][0] * 2 * 2)
                     off += shape[j][0]
                 views[i] = View(buf, _p(buf), shape[i][0], buf.shape[3], shape[i][1], shape[i][2])
             elif t == "yolo":
@@ -436,10 +445,17 @@ class Engine:
         self.sorted = torch.zeros(B, M, 8, device=dev, dtype=torch.int32)
         self.keep = torch.zeros(B, M, device=dev, dtype=torch.uint8)
         self.dets = torch.zeros(B * M, 8, device=dev, dtype=torch.int32)
-        self.det_counts = torch.zeros(B, device=dev, dtype=torch.int32)
-        # [class_kept | first_box] in one tensor so the host fetches both with one copy
-        self.seg_meta = torch.zeros(2, B, classes, device=dev, dtype=torch.int32)
+        # everything the host needs to know about a finished batch in ONE int32 block (one D2H copy):
+        # [detections kept per image (B) | their total (1) | kept per (image, class) | first box per (image, class)]
+        self.meta = torch.zeros(B + 1 + 2 * B * classes, device=dev, dtype=torch.int32)
+        self.det_counts = self.meta[:B]
+        self.det_counts_total = self.meta[:B + 1]
+        self.seg_meta = self.meta[B + 1:].view(2, B, classes)
         self.class_kept, self.first_box = self.seg_meta[0], self.seg_meta[1]
+        # y3_thresholds record (prob_thresh f32, pad, iou_thresh f64): the kernels read the thresholds from
+        # here at run time, so one captured graph per program serves every threshold setting
+        self.thresh = torch.zeros(16, device=dev, dtype=torch.uint8)
+        self._thresh_host = None
         self.class_start = torch.zeros(B, classes + 1, device=dev, dtype=torch.int32)
         self.dst_off = torch.zeros(B, classes, device=dev, dtype=torch.int32)
         self.out_tlbr = torch.empty(B * M, 4, device=dev, dtype=torch.int64)
@@ -524,29 +540,49 @@ class Engine:
         for d, logits in self.head_descs:
             _lib.yolo_decode_dense(d, logits, self.bbox, self.prob, self.cidx)
 
-    def _detect(self, prob_thresh, iou_thresh, compact=True, fused_stem=False):
-        """Backbone + decode + NMS (+ compaction).  Heads that can decode in their epilogue do; the
-        others (other class / anchor counts) write logits and run the stand-alone decode kernel."""
+    def set_thresholds(self, prob_thresh, iou_thresh):
+        """Update the device-resident ``y3_thresholds`` record (stream-ordered; a no-op when unchanged).
+        The source is pageable memory on purpose: the copy is staged before the call returns, so a later
+        update cannot overtake an earlier one that is still queued."""
+        want = (float(prob_thresh), float(iou_thresh))
+        if want != self._thresh_host:
+            rec = np.frombuffer(struct.pack("<ffd", want[0], 0.0, want[1]), dtype=np.uint8).copy()
+            self.thresh.copy_(torch.from_numpy(rec), non_blocking=True)
+            self._thresh_host = want
+
+    def _detect(self, prob_thresh=None, iou_thresh=None, compact=True, fused_stem=False, emit=False):
+        """Backbone + decode + NMS (+ compaction / final arrays).  Heads that can decode in their epilogue
+        do; the others (other class / anchor counts) write logits and run the stand-alone decode kernel.
+        Thresholds come from the device record; passing them here (eager callers only, never inside a
+        graph capture) updates it first."""
+        if prob_thresh is not None:
+            self.set_thresholds(prob_thresh, iou_thresh)
         self.counts.zero_()
-        self._prob_thresh = float(prob_thresh)
         self.run_backbone(fused_stem=fused_stem, fused_heads=True)
         for hk, (d, logits) in enumerate(self.head_descs):
             if not self.head_fused[hk]:
-                _lib.yolo_decode_cands(d, logits, prob_thresh, self.orig_hw, self.cands, self.counts, self.cap)
-        self._nms_tail(iou_thresh, compact)
+                _lib.yolo_decode_cands(d, logits, 0.0, self.orig_hw, self.cands, self.counts, self.cap,
+                                       dev_thresholds=self.thresh)
+        self._nms_tail(compact=compact, emit=emit)
 
     def _detect_tail(self, prob_thresh, iou_thresh, compact=True):
         """Decode (stand-alone kernels, from the logits of a previous run_backbone()) + NMS."""
+        self.set_thresholds(prob_thresh, iou_thresh)
         self.counts.zero_()
         for d, logits in self.head_descs:
-            _lib.yolo_decode_cands(d, logits, prob_thresh, self.orig_hw, self.cands, self.counts, self.cap)
-        self._nms_tail(iou_thresh, compact)
+            _lib.yolo_decode_cands(d, logits, 0.0, self.orig_hw, self.cands, self.counts, self.cap,
+                                   dev_thresholds=self.thresh)
+        self._nms_tail(compact=compact)
 
-    def _nms_tail(self, iou_thresh, compact=True):
-        _lib.nms(self.cands, self.counts, self.B, self.cap, self.num_classes, iou_thresh, 1, self.sorted, self.keep,
-                 self.first_box, self.nms_ws, class_start=self.class_start, class_kept=self.class_kept)
+    def _nms_tail(self, compact=True, emit=False):
+        _lib.nms(self.cands, self.counts, self.B, self.cap, self.num_classes, 0.0, 1, self.sorted, self.keep,
+                 self.first_box, self.nms_ws, class_start=self.class_start, class_kept=self.class_kept,
+                 dev_thresholds=self.thresh)
         if compact:  # flat y3_cand records (device-resident result; bench / multi-GPU gather)
             _lib.compact_kept(self.sorted, self.keep, self.counts, self.B, self.cap, self.dets, self.det_counts, 1)
+        if emit:  # the reference's final arrays, class groups ascending inside an image (see inference_batches)
+            _lib.plan_destinations(self.class_kept, self.B, self.num_classes, self.dst_off, self.det_counts_total)
+            self.emit()
 
     def emit(self, out=None):
         """Second, tiny launch of `inference`: write the kept records as the reference's final arrays
@@ -569,24 +605,35 @@ class Engine:
             def fn():
                 if self.stem is None:
                     pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self._detect(key[1], key[2], fused_stem=True)
+                self._detect(fused_stem=True)
         elif kind == "nms_u8":  # inference(): final arrays are emitted by a second launch (Engine.emit)
             def fn():
                 if self.stem is None:
                     pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
-                self._detect(key[1], key[2], compact=False, fused_stem=True)
+                self._detect(compact=False, fused_stem=True)
+        elif kind == "emit_u8":  # inference_batches(): final arrays (classes ascending) inside the same graph
+            def fn():
+                if self.stem is None:
+                    pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                self._detect(compact=False, fused_stem=True, emit=True)
         elif kind == "det_f32":
             def fn():
                 pack_f32(self.in_f32, self.in_view.buf, self.in_view.C)
-                self._detect(key[1], key[2])
+                self._detect()
         else:
             raise KeyError(kind)
         return fn
 
     def launch(self, key):
-        """Run program ``key`` on the current stream (CUDA-graph replay after the first call)."""
+        """Run program ``key`` on the current stream (CUDA-graph replay after the first call).
+        ``key`` = ``(kind,)`` or ``(kind, prob_thresh, iou_thresh)``; thresholds are not part of the
+        graph (they live in the device record), so every setting replays the same graph."""
         if self.dry:
             raise RuntimeError("this plan was built on the meta device and cannot run")
+        if len(key) == 3:
+            with torch.cuda.device(self.device):
+                self.set_thresholds(key[1], key[2])
+        key = key[:1]
         ent = self._graphs.get(key)
         if ent is None:
             fn = self._program(key)
@@ -603,7 +650,9 @@ class Engine:
                 if self.use_graphs:
                     torch.cuda.synchronize(self.device)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
+                    # thread_local: a CUDA call made by ANOTHER thread during the capture (ProcessGroupNCCL's
+                    # watchdog polling events, a data-loader thread pinning memory) must not invalidate it
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                         fn()
                 _lib.set_pdl(pdl_before)
             ent = (fn, graph, launches)
@@ -616,7 +665,7 @@ class Engine:
 
     def launches(self, key):
         """Kernels launched by one run of program ``key`` (bench.py's gpu_launches)."""
-        return self._graphs[key][2]
+        return self._graphs[key[:1]][2]
 
     # -- Darknet.forward ---------------------------------------------------------------------
     def forward_dense(self, x):
@@ -634,6 +683,55 @@ class Engine:
             self.launch((kind, float(prob_thresh), float(iou_thresh)))
         return self.dets, self.det_counts, self.first_box
 
+    def memory_bound_ops(self):
+        """(name, launch closure, algorithmic HBM bytes) of every memory-bound kernel of this plan: the
+        pooling / elementwise block kernels that were not fused away, the input packing kernels and the
+        dense YOLO decode of ``Darknet.forward`` (bench.py's ``hbm_roofline``)."""
+        ops = list(self.mem_ops)
+        px = self.B * self.H * self.W
+        cin = self.net.net_info["channels"]
+        pack_f32 = _lib.im2col3x3_nchw_f32 if self.first_im2col else _lib.pack_nchw_f32
+        ops.append((pack_f32.__name__, lambda: pack_f32(self.in_f32, self.in_view.buf, self.in_view.C),
+                    px * (cin * 4 + self.in_view.C * 2)))
+        if self.in_u8 is not None and self.stem is None:
+            pack_u8 = _lib.im2col3x3_bgr_u8 if self.first_im2col else _lib.pack_bgr_u8
+            ops.append((pack_u8.__name__, lambda: pack_u8(self.in_u8, self.in_view.buf, self.in_view.C),
+                        px * (3 + self.in_view.C * 2)))
+        for hk, (d, logits) in enumerate(self.head_descs):
+            boxes = d.n * d.num_anchors * d.g_h * d.g_w
+            fields = d.num_anchors * (5 + d.num_classes)
+            ops.append((f"yolo_decode_dense[{d.g_h}x{d.g_w}]",
+                        lambda d=d, logits=logits: _lib.yolo_decode_dense(d, logits, self.bbox, self.prob, self.cidx),
+                        d.n * d.g_h * d.g_w * fields * 4 + boxes * (16 + 4 + 8)))
+        return ops
+
+    def time_convs_in_sequence(self, passes=5):
+        """Device time of every convolution launch measured INSIDE one in-order pass over the network:
+        CUDA events are recorded between consecutive launches, so every kernel finds the L2 in the state
+        its real predecessor left it in (``time_convs`` replays one launch back to back, which keeps small
+        layers' operands L2-warm and flatters them).  A spin kernel in front gives the host a head start so
+        the device never waits for a launch.  Returns (seconds per forward summed over convs — median pass,
+        [(block, seconds, flops)])."""
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.Stream(device=self.device)
+            n = len(self.conv_ops)
+            rows = []
+            with torch.cuda.stream(stream):
+                for _ in range(passes + 1):  # first pass = warm-up
+                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+                    torch.cuda._sleep(20_000_000)  # ~10 ms
+                    evs[0].record(stream)
+                    for j, (_, fn, _) in enumerate(self.conv_ops):
+                        fn()
+                        evs[j + 1].record(stream)
+                    stream.synchronize()
+                    rows.append([evs[j].elapsed_time(evs[j + 1]) * 1e-3 for j in range(n)])
+            rows = rows[1:]
+            order = sorted(range(len(rows)), key=lambda r: sum(rows[r]))
+            med = rows[order[len(order) // 2]]
+            per = [(blk, med[j], flops) for j, (blk, _, flops) in enumerate(self.conv_ops)]
+            return sum(med), per
+
     def time_convs(self, iters=10):
         """Device time of every convolution launch, each timed ALONE: the launch is captured
         `iters` times into a small CUDA graph (so host launch latency does not pace the
@@ -647,7 +745,7 @@ class Engine:
                     fn()
                     stream.synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=stream):
+                    with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
                         for _ in range(iters):
                             fn()
                     g.replay()

@@ -1,17 +1,20 @@
 """Inference entry points — host-side mirror of the hot-path half of ``yolov3/inference.py`` of
 nrsyed/pytorch-yolov3 (``inference`` :286-368, ``non_max_suppression`` :220-266,
 ``cxywh_to_tlbr`` :269-283), with identical argument meaning, threshold semantics
-(keep ``prob >= prob_thresh``, suppress ``iou > nms_iou_thresh``) and return structures.
+(keep ``prob >= prob_thresh``, suppress ``iou > nms_iou_thresh``) and return structures, plus
+``inference_batches`` — the batched, pipelined loop the reference's CLI leaves as a TODO
+(``# TODO: batch images``, yolov3/__main__.py:157; frame loops yolov3/inference.py:435-544).
 
 Everything between the uint8 images and the kept detections runs on the GPU in one CUDA-graph
 replay: BGR->RGB /255 packing, the Darknet forward, YOLO decode + threshold + pixel scaling +
-integer truncation + tl/br conversion, per-class NMS and compaction.  The host copies the
-images up (pinned memory), reads back how many detections every (image, class) group kept, tells
-the device where each group goes (class groups follow the reference's ``set(class_idx)`` visiting
-order) and receives the final int64 / float32 arrays.  There is no CPU implementation here.
+integer truncation + tl/br conversion, per-class NMS and the final int64 / float32 arrays.  The
+host copies the images up (pinned memory), reads back how many detections every image kept and
+receives the arrays; class groups follow the reference's ``set(class_idx)`` visiting order.
+There is no CPU implementation here.
 """
 import os
 import time
+from collections import deque
 
 import numpy as np
 import torch
@@ -99,11 +102,43 @@ def _stack_into(dst, images):
     _lib.stage_images(dst, images, _STAGE_THREADS)
 
 
+def _prepare(net, images, resize):
+    """Argument handling shared by ``inference`` and ``inference_batches`` (reference:
+    yolov3/inference.py:314-326): list-wrap, remember the original shapes, optional cv2 resize to the
+    cfg's ``[net]`` size, shape / dtype validation.  Returns (images, orig_shapes, B, H, W)."""
+    if not isinstance(images, (list, tuple)):
+        images = [images]
+    images = list(images)
+    orig_shapes = [im.shape for im in images]
+    if resize:
+        import cv2
+        net_shape = (net.net_info["height"], net.net_info["width"])
+        images = [cv2.resize(im, net_shape) if im.shape[:2] != net_shape else im for im in images]
+    if images[0].ndim != 3 or images[0].shape[2] != 3:
+        raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got shape {images[0].shape}")
+    first = images[0].shape
+    for im in images:
+        if im.shape != first:  # the reference fails in np.stack with this error type
+            raise ValueError("all input arrays must have the same shape")
+        if im.dtype != np.uint8:
+            raise ValueError(f"images must be uint8, got {im.dtype}")
+    return images, orig_shapes, len(images), first[0], first[1]
+
+
+def _split_meta(m, B, C):
+    """Host copy of ``Engine.meta`` -> (per_image [B], total, class_kept [B,C], first_box [B,C])."""
+    return m[:B], int(m[B]), m[B + 1:B + 1 + B * C].reshape(B, C), m[B + 1 + B * C:].reshape(B, C)
+
+
+def _empty_result():
+    return [np.zeros((0, 4), np.int64), np.zeros(0, np.float32), np.zeros(0, np.int64)]
+
+
 def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True):
     """Run the network on image(s); same contract as the reference (yolov3/inference.py:286-368).
 
     Args:
-        net: ``yolov3_b200.Darknet``.
+        net: ``yolov3_b200.Darknet`` (in eval mode).
         images: one ``HxWx3`` uint8 BGR array or a list of them (one batch).
         device: CUDA device string; must be the device ``net`` runs on.
         prob_thresh: detections with ``class_prob >= prob_thresh`` are kept.
@@ -113,50 +148,42 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
 
     Returns:
         list (one entry per image) of ``[bbox_tlbr int64 (K,4), class_prob float32 (K,),
-        class_idx int64 (K,)]`` in ORIGINAL-image pixels, unclipped, ordered like the reference.
+        class_idx int64 (K,)]`` in ORIGINAL-image pixels, unclipped, ordered like the reference
+        (class groups in ``set(class_idx)`` order, descending probability inside a group; equal
+        probabilities inside a class are visited in ascending box order — the reference's
+        ``np.argsort`` leaves that order unspecified).  Coordinates are exact while they fit in int32
+        (they saturate beyond, i.e. for ``exp(tw) * anchor`` above ~2e9 pixels).
     """
     t_enter = time.perf_counter()
-    if not isinstance(images, list):
-        images = [images]
     dev = _lib.require_device(device)
-    orig_shapes = [im.shape for im in images]
-    if resize:
-        import cv2
-        net_shape = (net.net_info["height"], net.net_info["width"])
-        images = [cv2.resize(im, net_shape) if im.shape[:2] != net_shape else im for im in images]
-    if images[0].ndim != 3 or images[0].shape[2] != 3:
-        raise ValueError(f"images must be HxWx3 uint8 BGR arrays, got shape {images[0].shape}")
-    B, (H, W, _) = len(images), images[0].shape
-    first = images[0].shape
-    for im in images:
-        if im.shape != first:  # the reference fails in np.stack with this error type
-            raise ValueError("all input arrays must have the same shape")
-        if im.dtype != np.uint8:
-            raise ValueError(f"images must be uint8, got {im.dtype}")
+    net.check_fresh()
+    images, orig_shapes, B, H, W = _prepare(net, images, resize)
 
-    # (The sub-batch plans keep programmatic dependent launch: their kernels are short, and the latency at
-    # every kernel boundary costs more than a parked dependent CTA — measured +5-8 % end to end.)
     # Large batches go through the GPU as a few sub-batches on their own streams and plans: while
     # sub-batch k computes, the host stages and uploads k+1 and finishes k-1 (destinations, emit,
-    # download) — the synchronous call hides most of its own host and PCIe time.
+    # download) — the synchronous call hides most of its own host and PCIe time.  (The sub-batch plans
+    # keep programmatic dependent launch: their kernels are short, and the latency at every kernel
+    # boundary costs more than a parked dependent CTA — measured +5-8 % end to end.)
     spans = _sub_batches(B)
-    io = net.__dict__.setdefault("_host_io", {}).get((B, H, W, str(dev)))
+    geom = net.geometry(B, H, W)
+    io = geom.get("io")
     if io is None:
-        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if len(spans) > 1 else 0)
+        multi = len(spans) > 1
+        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if multi else 0)
         if eng0.device != dev:
             raise RuntimeError(f"net runs on {eng0.device}, inference(device='{device}') requested")
         with torch.cuda.device(dev):
             C, M = eng0.num_classes, eng0.M
+            engines = [net.engine(hi - lo, H, W, slot=(k + 1) if multi else 0) for k, (lo, hi) in enumerate(spans)]
             io = {"img": _pinned((B, H, W, 3), torch.uint8), "hw": _pinned((B, 2), torch.int32),
-                  "meta": [_pinned((2, hi - lo, C), torch.int32) for lo, hi in spans],
+                  "meta": [_pinned((e.meta.numel(),), torch.int32) for e in engines],
                   "dst": [_pinned((hi - lo, C), torch.int32) for lo, hi in spans],
-                  "engines": [net.engine(hi - lo, H, W, slot=(k + 1) if len(spans) > 1 else 0)
-                              for k, (lo, hi) in enumerate(spans)],
-                  "streams": [torch.cuda.Stream(device=dev) for _ in spans] if len(spans) > 1 else [None],
+                  "engines": engines,
+                  "streams": [torch.cuda.Stream(device=dev) for _ in spans] if multi else [None],
                   "out": (torch.empty(B * M, 4, device=dev, dtype=torch.int64),
                           torch.empty(B * M, device=dev, dtype=torch.float32),
-                          torch.empty(B * M, device=dev, dtype=torch.int64)) if len(spans) > 1 else None}
-        net._host_io[(B, H, W, str(dev))] = io
+                          torch.empty(B * M, device=dev, dtype=torch.int64)) if multi else None}
+        geom["io"] = io
     engines = io["engines"]
     if engines[0].device != dev:
         raise RuntimeError(f"net runs on {engines[0].device}, inference(device='{device}') requested")
@@ -183,7 +210,7 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
                 eng.in_u8.copy_(io["img"][lo:hi], non_blocking=True)
                 eng.orig_hw.copy_(io["hw"][lo:hi], non_blocking=True)
                 eng.launch(key)
-                meta.copy_(eng.seg_meta, non_blocking=True)  # kept per (image, class) + first box per class
+                meta.copy_(eng.meta, non_blocking=True)  # kept per (image, class) + first box per class
             mark(f"launched {lo}:{hi}")
         # phase 2: per sub-batch, as soon as its NMS is done: destinations -> emit -> download
         base = 0
@@ -191,13 +218,13 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
         for (lo, hi), eng, st, meta, dstbuf in zip(spans, engines, streams, io["meta"], io["dst"]):
             st.synchronize()
             mark(f"nms done {lo}:{hi}")
-            m = meta.numpy()
-            dst_off, per_image = _destinations(m[0], m[1])
+            _, _, class_kept, first_box = _split_meta(meta.numpy(), eng.B, eng.num_classes)
+            dst_off, per_image = _destinations(class_kept, first_box)
             total = int(per_image.sum())
             eng.last_per_image = per_image
             if total == 0:
                 for i in range(lo, hi):
-                    results[i] = [np.zeros((0, 4), np.int64), np.zeros(0, np.float32), np.zeros(0, np.int64)]
+                    results[i] = _empty_result()
                 continue
             # results live in fresh pinned arrays (torch's caching host allocator recycles them once
             # the caller drops the result), so the device writes the final dtypes and nothing is re-copied
@@ -240,7 +267,6 @@ def _sub_batches(batch):
     well, so the spans grow: 1/8, 3/8, 1/2 of the batch from 32 images, two halves from 16, otherwise
     the whole batch.  ``Y3_SUB_BATCHES=n`` forces n equal spans, ``Y3_SUB_SPLIT=a,b,c`` explicit sizes
     (scaled to the batch)."""
-    import os
     split = os.environ.get("Y3_SUB_SPLIT", "")
     n = int(os.environ.get("Y3_SUB_BATCHES", "0"))
     if split:
@@ -264,13 +290,147 @@ def _sub_batches(batch):
 
 def last_device_outputs(net, batch, height, width, device):
     """Device-resident final arrays of the last ``inference`` call with this geometry:
-    ``(tlbr int64 [K,4], prob float32 [K], cls int64 [K], per_image int64 numpy [B])`` — what
-    ``distributed.gather_outputs`` sends between GPUs without a host round trip."""
-    io = net._host_io[(batch, height, width, str(_lib.require_device(device)))]
+    ``(tlbr int64 [K,4], prob float32 [K], cls int64 [K], per_image int64 numpy [B])``."""
+    io = net.geometry(batch, height, width)["io"]
     eng = io["engines"][0]
     o = io["out"] if io["out"] is not None else (eng.out_tlbr, eng.out_prob, eng.out_cls)
     k = io["last_total"]
     return o[0][:k], o[1][:k], o[2][:k], io["last_per_image"]
+
+
+# ----------------------------------------------------------------------------------------------
+# batched, pipelined loop (SURVEY.md §8f #4: the CLI's image-directory / frame loops)
+# ----------------------------------------------------------------------------------------------
+class _Slot:
+    """One in-flight batch of ``inference_batches``: its own execution plan (buffers + CUDA graph),
+    stream and pinned staging memory."""
+
+    def __init__(self, net, B, H, W, index, dev):
+        # plans that run side by side on different streams are captured without programmatic dependent
+        # launch (a parked dependent CTA would hold an SM the neighbouring batch could use)
+        self.eng = net.engine(B, H, W, slot=100 + index, concurrent=True)
+        if self.eng.device != dev:
+            raise RuntimeError(f"net runs on {self.eng.device}, device '{dev}' requested")
+        self.stream = torch.cuda.Stream(device=dev)
+        self.img = _pinned((B, H, W, 3), torch.uint8)
+        self.hw = _pinned((B, 2), torch.int32)
+        self.meta = _pinned((self.eng.meta.numel(),), torch.int32)
+        self.ev_meta = torch.cuda.Event()
+        self.ev_out = torch.cuda.Event()
+
+
+def _reorder_to_set_order(res, class_kept_row, first_box_row):
+    """One image's arrays, emitted with class groups ascending, re-ordered to the reference's
+    ``set(class_idx)`` group order (needed only when fewer than 19 classes are present, see
+    ``_set_order``)."""
+    order = _set_order(first_box_row)
+    if order.size < 2 or np.all(order[1:] > order[:-1]):
+        return res
+    kept = class_kept_row.astype(np.int64)
+    starts = np.cumsum(kept) - kept
+    lens = kept[order]
+    offs = np.cumsum(lens) - lens
+    perm = np.arange(int(lens.sum()), dtype=np.int64) + np.repeat(starts[order] - offs, lens)
+    return [res[0][perm], res[1][perm], res[2][perm]]
+
+
+def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True, depth=3,
+                      gather=None):
+    """``inference`` over a stream of batches, pipelined: a generator that yields, in order, exactly
+    what ``inference(net, batch, ...)`` returns for every batch of ``batches`` (an iterable of image
+    lists; a bare ndarray counts as a one-image batch).
+
+    While batch k runs on the GPU (one CUDA-graph replay on its own stream and plan), the host stages
+    and uploads batch k+1 and downloads / hands out batch k-1, so neither PCIe nor host work sits
+    between two batches' kernels.  Up to ``depth`` batches are in flight (>= 2; each holds one plan:
+    activations + graph).  The final int64 / float32 arrays are written on the device inside the same
+    graph (class groups ascending) and land in pinned host arrays; images whose ``set(class_idx)``
+    order is not ascending (fewer than 19 distinct classes) are re-ordered on the host.
+
+    ``gather``: optional ``distributed.DetectionGather`` — every batch's kept detections are also
+    gathered, device to device, on its destination rank (all ranks must iterate in lock step).
+    """
+    dev = _lib.require_device(device)
+    depth = max(2, int(depth))
+    pending = deque()
+    thr = (float(prob_thresh), float(nms_iou_thresh))
+    counters = {}
+
+    def submit(images):
+        net.check_fresh()
+        images, orig_shapes, B, H, W = _prepare(net, images, resize)
+        geom = net.geometry(B, H, W)
+        slots = geom.setdefault("pipe", [])
+        idx = counters.get((B, H, W), 0)
+        counters[(B, H, W)] = idx + 1
+        with torch.cuda.device(dev):
+            if len(slots) <= idx % depth:
+                slots.append(_Slot(net, B, H, W, len(slots), dev))
+            slot = slots[idx % depth]
+            while any(it["slot"] is slot for it in pending):  # only when geometries alternate oddly
+                yield_ready.append(finish(pending.popleft()))
+            _stack_into(slot.img.numpy(), images)
+            slot.hw.numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
+            eng = slot.eng
+            with torch.cuda.stream(slot.stream):
+                eng.in_u8.copy_(slot.img, non_blocking=True)
+                eng.orig_hw.copy_(slot.hw, non_blocking=True)
+                eng.launch(("emit_u8",) + thr)
+                slot.meta.copy_(eng.meta, non_blocking=True)
+                if gather is not None:
+                    gather.post_counts(eng)
+                slot.ev_meta.record()
+        return {"slot": slot, "B": B, "stage": 0}
+
+    def stage_a(it):
+        """Batch finished on the GPU: read its counts, queue the download of exactly its detections."""
+        slot, B = it["slot"], it["B"]
+        eng = slot.eng
+        slot.ev_meta.synchronize()
+        per_image, total, class_kept, first_box = _split_meta(slot.meta.numpy(), B, eng.num_classes)
+        it["per_image"] = per_image.copy()
+        it["total"] = total
+        odd = np.nonzero(((first_box != _INT32_MAX).sum(axis=1) < 19) | (eng.num_classes > 128))[0]
+        it["odd"] = [(int(i), class_kept[i].copy(), first_box[i].copy()) for i in odd]
+        with torch.cuda.device(dev), torch.cuda.stream(slot.stream):
+            if total:
+                cap = (total + 16383) // 16384 * 16384
+                it["out"] = (_pinned((cap, 4), torch.int64)[:total], _pinned((cap,), torch.float32)[:total],
+                             _pinned((cap,), torch.int64)[:total])
+                it["out"][0].copy_(eng.out_tlbr[:total], non_blocking=True)
+                it["out"][1].copy_(eng.out_prob[:total], non_blocking=True)
+                it["out"][2].copy_(eng.out_cls[:total], non_blocking=True)
+            if gather is not None:
+                gather.gather_payload(eng, total)
+            slot.ev_out.record()
+        it["stage"] = 1
+
+    def finish(it):
+        if it["stage"] == 0:
+            stage_a(it)
+        it["slot"].ev_out.synchronize()
+        if not it["total"]:
+            return [_empty_result() for _ in range(it["B"])]
+        tlbr, prob, cls = (t.numpy() for t in it["out"])
+        results, pos = [], 0
+        for k in it["per_image"].tolist():
+            results.append([tlbr[pos:pos + k], prob[pos:pos + k], cls[pos:pos + k]])
+            pos += k
+        for i, ck, fb in it["odd"]:
+            results[i] = _reorder_to_set_order(results[i], ck, fb)
+        return results
+
+    yield_ready = []
+    for images in batches:
+        pending.append(submit(images))
+        while yield_ready:
+            yield yield_ready.pop(0)
+        if len(pending) >= 2 and pending[-2]["stage"] == 0:
+            stage_a(pending[-2])
+        while len(pending) >= depth:
+            yield finish(pending.popleft())
+    while pending:
+        yield finish(pending.popleft())
 
 
 def non_max_suppression(bbox_tlbr, class_prob, class_idx=None, iou_thresh=0.3):
@@ -279,8 +439,10 @@ def non_max_suppression(bbox_tlbr, class_prob, class_idx=None, iou_thresh=0.3):
     given (descending probability inside a class), class-agnostic otherwise.
 
     Args:
-        bbox_tlbr: ``Mx4`` integer array (x1, y1, x2, y2); |coordinates| < 2**31.
-        class_prob: ``M`` probabilities.
+        bbox_tlbr: ``Mx4`` integer array (x1, y1, x2, y2); |coordinates| < 2**31 (the reference
+            computes in int64; this implementation stores int32 records and raises beyond).
+        class_prob: ``M`` probabilities.  Equal probabilities are visited in ascending index order
+            (the reference's ``np.argsort(...)[::-1]`` leaves tie order unspecified).
         class_idx: ``M`` class indices in ``[0, 1024)`` or ``None``.
         iou_thresh: boxes with ``iou > iou_thresh`` w.r.t. a kept box are dropped.
     """

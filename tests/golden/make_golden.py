@@ -34,6 +34,7 @@ from yolov3 import inference as ref_inference  # noqa: E402
 from oracle import darknet_oracle as DO  # noqa: E402
 from oracle import postprocess_oracle as PO  # noqa: E402
 from oracle import nms_c  # noqa: E402
+from oracle import bf16_matched as BM  # noqa: E402
 
 torch.manual_seed(0)
 torch.set_num_threads(1)  # fixed reduction order for the stored float vectors
@@ -249,6 +250,71 @@ def synth_decoded(rng, B, M, classes):
     return {"bbox_xywh": np.concatenate([xy, wh], axis=2), "class_prob": prob, "class_idx": idx}
 
 
+def golden_bf16_matched():
+    """The bf16-matched oracle (oracle/bf16_matched.py) against the same thing built from the
+    reference's OWN modules (SURVEY.md §8c last row): deep copy of the reference net, BatchNorm folded
+    into conv.weight (rounded to bf16) and turned into a pure bias, forward hooks rounding block
+    outputs to bf16 at the plan's rounding points."""
+    import copy
+    cfg = os.path.join(HERE, "micro.cfg")
+    blocks, net_info = DO.load_model(cfg)
+    wpath = os.path.join(HERE, "micro.weights")
+    net = copy.deepcopy(ref.Darknet(cfg, device="cpu").load_weights(wpath).eval())
+    _, params = DO.read_weights(wpath, blocks, net_info)
+    fused = BM.single_consumer_shortcuts(blocks)
+    hooks = []
+    for i, (b, m) in enumerate(zip(net.blocks, net.modules_)):
+        if b["type"] != "convolutional":
+            continue
+        conv = m[0]
+        W, bias = BM.fold_bn(params[i])
+        with torch.no_grad():
+            conv.weight.copy_(BM.bf16(W))
+            if len(m) > 1 and isinstance(m[1], torch.nn.BatchNorm2d):
+                bn = m[1]
+                # gamma = 1, mean = 0, var = 1 - eps: (x - 0) / sqrt((1 - eps) + eps) * 1 + b' (SURVEY.md §8c)
+                bn.weight.fill_(1.0), bn.running_mean.zero_(), bn.running_var.fill_(1.0 - bn.eps)
+                assert float(torch.sqrt(bn.running_var[0] + bn.eps)) == 1.0
+                bn.bias.copy_(bias)
+            else:
+                conv.bias.copy_(bias)
+        head = i + 1 < len(blocks) and blocks[i + 1]["type"] == "yolo"
+        hooks.append(m.register_forward_pre_hook(lambda mod, inp: (BM.bf16(inp[0]),)))
+        if not (head or i in fused):
+            hooks.append(m.register_forward_hook(lambda mod, inp, out: BM.bf16(out)))
+    # the reference adds shortcuts inline (darknet.py:376-379): round their result through a wrapper
+    # around torch.Tensor.__add__ is not possible from outside, so the reference forward is replayed
+    # block by block with ITS modules and ITS cache rule, rounding the shortcut sums.
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(2, 3, 64, 64, generator=g)
+    cached, outs = {}, []
+    xx = BM.bf16(x.clone())
+    with torch.no_grad():
+        for i, b in enumerate(net.blocks):
+            t = b["type"]
+            if t in ("convolutional", "maxpool", "upsample"):
+                xx = net.modules_[i](xx)
+            elif t == "route":
+                xx = torch.cat(tuple(cached[j] for j in b["layers"]), dim=1)
+            elif t == "shortcut":
+                xx = BM.bf16(cached[i - 1] + cached[i + b["from"]])
+            elif t == "yolo":
+                outs.append(net.modules_[i][0](xx))
+            if i in net.blocks_to_cache:
+                cached[i] = xx
+        bbox = torch.cat([o[0] for o in outs], dim=1)
+        bbox[:, :, 2:4] /= torch.tensor([net.net_info["width"], net.net_info["height"]])
+        rprob, ridx = torch.cat([o[1] for o in outs], dim=1), torch.cat([o[2] for o in outs], dim=1)
+        o = BM.forward(x.clone(), blocks, net_info, params)
+    for h in hooks:
+        h.remove()
+    # BN as a pure bias goes through batch_norm's (x - 0) / sqrt(1) * 1 + b': exact
+    assert torch.equal(o["bbox_xywh"], bbox) and torch.equal(o["class_prob"], rprob) and torch.equal(o["class_idx"], ridx)
+    np.savez_compressed(os.path.join(HERE, "micro_bf16_matched.npz"), x=x.numpy(), bbox_xywh=bbox.numpy(),
+                        class_prob=rprob.numpy(), class_idx=ridx.numpy())
+    print("bf16-matched oracle == reference modules with fold + rounding hooks (micro.cfg): identical")
+
+
 def golden_postprocess():
     rng = np.random.default_rng(99)
     store = {}
@@ -342,6 +408,7 @@ if __name__ == "__main__":
     golden_maxpool()
     golden_yolo_decode()
     golden_micro_network()
+    golden_bf16_matched()
     golden_postprocess()
     golden_nms()
     golden_preprocess()

@@ -752,7 +752,7 @@ def test_fused_head_decode_equals_standalone_decode(yolov3_full):
         return out
 
     eng.counts.zero_()
-    eng._prob_thresh = thr
+    eng.set_thresholds(thr, 0.3)
     eng.run_backbone(fused_stem=True, fused_heads=True)
     fused = snapshot()
     eng.run_backbone(fused_stem=True, fused_heads=False)

@@ -154,3 +154,22 @@ def test_micro_inference_end_to_end():
         want = {tuple(t) + (int(c),) for t, c in zip(z[f"img{i}_tlbr"].tolist(), z[f"img{i}_cls"])}
         got = {tuple(t) + (int(c),) for t, c in zip(r[0].tolist(), r[2])}
         assert len(want ^ got) <= 0.02 * len(want)
+
+
+def test_bf16_matched_oracle_equals_reference_modules_with_rounding_hooks():
+    """oracle/bf16_matched.py vs the golden built from the reference's OWN modules (deep copy, BN folded
+    into conv.weight, bf16 rounding hooks; tests/golden/make_golden.py::golden_bf16_matched)."""
+    from oracle import bf16_matched as BM
+    z = np.load(os.path.join(GOLDEN, "micro_bf16_matched.npz"))
+    blocks, net_info = DO.load_model(os.path.join(GOLDEN, "micro.cfg"))
+    _, params = DO.read_weights(os.path.join(GOLDEN, "micro.weights"), blocks, net_info)
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        o = BM.forward(torch.from_numpy(z["x"]), blocks, net_info, params)
+    assert np.allclose(o["bbox_xywh"].numpy(), z["bbox_xywh"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(o["class_prob"].numpy(), z["class_prob"], rtol=1e-5, atol=1e-7)
+    assert (o["class_idx"].numpy() != z["class_idx"]).mean() < 1e-3
+    # and it is NOT the fp32 forward: rounding moves the heads measurably
+    with torch.no_grad():
+        f = DO.forward(torch.from_numpy(z["x"]), blocks, net_info, params)
+    assert float((f["class_prob"] - o["class_prob"]).abs().max()) > 1e-4

@@ -56,7 +56,8 @@ def main():
 
     def nms():
         _lib.nms(eng.cands, eng.counts, eng.B, eng.cap, eng.num_classes, bench.IOU_THRESH, 1, eng.sorted, eng.keep,
-                 eng.first_box, eng.nms_ws, class_start=eng.class_start, class_kept=eng.class_kept)
+                 eng.first_box, eng.nms_ws, class_start=eng.class_start, class_kept=eng.class_kept,
+                 dev_thresholds=eng.thresh)
 
     def compact():
         _lib.compact_kept(eng.sorted, eng.keep, eng.counts, eng.B, eng.cap, eng.dets, eng.det_counts, 1)
