@@ -318,3 +318,67 @@ def test_nccl_detection_gather_content_two_ranks(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     d = json.load(open(out))
     assert d["ok"] and d["batches"] >= 3 and d["detections"] > 1000
+
+
+# ------------------------------------------------------------------------------------------
+# CLI drop-in: our batched CLI, and the reference's unmodified CLI re-bound
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tiny_on_disk(tmp_path_factory):
+    import cv2
+    net, blocks, net_info, params = build_full("yolov3-tiny", 416, tmp_path_factory)
+    d = tmp_path_factory.mktemp("imgs")
+    rng = np.random.default_rng(11)
+    shapes = [(416, 416), (375, 500), (480, 640), (416, 416), (300, 300), (427, 640), (416, 416)]
+    for i, (h, w) in enumerate(shapes):
+        cv2.imwrite(str(d / f"img{i:02d}.png"), rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    wpath = str(tmp_path_factory.mktemp("w2") / "tiny.weights")
+    DO.write_weights(wpath, params, blocks, net_info)
+    return net, str(d), wpath
+
+
+def test_cli_batched_image_directory_equals_per_image_inference(tiny_on_disk, tmp_path):
+    import cv2
+    from yolov3_b200 import cli
+    net, image_dir, wpath = tiny_on_disk
+    out = tmp_path / "dets.json"
+    cfg = os.path.join(MODELS, "yolov3-tiny.cfg")
+    dump = cli.main(["-I", image_dir, "-c", cfg, "-w", wpath, "-d", "cuda:0", "-p", "0.2", "-b", "3", "--no-display",
+                     "--save-json", str(out), "-n", os.path.join(MODELS, "coco.names")])
+    on_disk = json.load(open(out))
+    assert sorted(on_disk) == sorted(os.listdir(image_dir)) and len(on_disk) == 7
+    total = 0
+    for fname in sorted(os.listdir(image_dir)):
+        img = cv2.imread(os.path.join(image_dir, fname))
+        want = yolov3_b200.inference(net, img, device="cuda:0", prob_thresh=0.2, nms_iou_thresh=0.3)[0]  # resize=True
+        assert np.array_equal(np.asarray(dump[fname]["bbox_tlbr"]).reshape(-1, 4), want[0])
+        assert np.array_equal(np.asarray(on_disk[fname]["class_idx"], dtype=np.int64), want[2])
+        total += len(want[1])
+    assert total > 50
+    # `python -m yolov3` resolves to the same entry point when the alias package is first on the path
+    r = subprocess.run([sys.executable, "-m", "yolov3", "-I", os.path.join(image_dir, "img00.png"), "-c", cfg, "-w", wpath,
+                        "-d", "cuda:0", "--no-display", "-v"], capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "PYTHONPATH": os.path.join(ROOT, "pytorch-yolov3_b200")})
+    assert r.returncode == 0 and "1 images" in r.stdout, r.stdout[-500:] + r.stderr[-2000:]
+
+
+def test_cli_reference_main_unmodified_on_rebound_hot_path(tiny_on_disk, tmp_path):
+    """INTEGRATION.md recipe (b), executed: the reference's own yolov3/__main__.py (baseline/_ref) runs
+    unmodified with Darknet / inference re-bound; what it hands to draw_boxes is our inference()."""
+    import cv2
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "yolov3")):
+        pytest.skip("baseline/_ref (pip-installed reference) not present")
+    net, image_dir, wpath = tiny_on_disk
+    out = tmp_path / "ref_cli.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cli_reference_main_check.py"), image_dir,
+                        os.path.join(MODELS, "yolov3-tiny.cfg"), wpath, str(out)], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-3000:]
+    assert "Running model on" in r.stdout
+    d = json.load(open(out))
+    assert len(d["drawn"]) == len(d["files"]) == 7
+    for fname, drawn in zip(d["files"], d["drawn"]):  # the reference iterates os.listdir order
+        img = cv2.imread(os.path.join(image_dir, fname))
+        want = yolov3_b200.inference(net, img, device="cuda:0", prob_thresh=0.2, nms_iou_thresh=0.3)[0]
+        assert np.array_equal(np.asarray(drawn["bbox"]).reshape(-1, 4), want[0])
+        assert np.array_equal(np.asarray(drawn["cls"], dtype=np.int64), want[2])
