@@ -756,8 +756,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         main_reference(args, rank, world)
-    else:
+        return
+    from yolov3_b200 import _lib
+    rec = _lib.enable_trap_record(torch.device("cuda", local_rank))  # where a kernel watchdog trap would be recorded
+    try:
         main_ours(args, rank, local_rank, world)
+    except BaseException:
+        note = _lib.describe_trap_record(rec)
+        if note:
+            print(f"[rank {rank}] {note}", file=sys.stderr, flush=True)
+        raise
 
 
 if __name__ == "__main__":

@@ -166,6 +166,14 @@ int y3_stage_images(void* dst, const void* const* srcs, int32_t n, int64_t bytes
   return Y3_OK;
 }
 
+int y3_debug_set_trap_record(void* host_mapped) {
+  unsigned long long* p = static_cast<unsigned long long*>(host_mapped);
+  Y3_CUDA_OK(y3::conv_umma_set_trap_record(p));
+  Y3_CUDA_OK(y3::conv_patch_set_trap_record(p));
+  Y3_CUDA_OK(y3::conv_chain_set_trap_record(p));
+  return Y3_OK;
+}
+
 long long y3_launch_count(void) { return y3::g_launches; }
 void y3_reset_launch_count(void) { y3::g_launches = 0; }
 

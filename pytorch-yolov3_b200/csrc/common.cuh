@@ -54,6 +54,11 @@ int encode_tiled_map(void* map, int rank, const void* base, const uint64_t* dims
 int conv3x3_patch_try(const ::y3_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
                       void* y, cudaStream_t stream);
 
+// watchdog record pointer of each translation unit that waits on mbarriers (ptx.cuh: mbar_timeout)
+cudaError_t conv_umma_set_trap_record(unsigned long long* host_mapped);
+cudaError_t conv_patch_set_trap_record(unsigned long long* host_mapped);
+cudaError_t conv_chain_set_trap_record(unsigned long long* host_mapped);
+
 int num_sms();  // SM count of the current device (cached per device)
 bool pdl_enabled();  // programmatic dependent launch on every kernel (Y3_NO_PDL=1 / y3_set_pdl(0) turn it off)
 void set_pdl(int on);

@@ -21,6 +21,7 @@
 // Weights of both layers stay resident in smem for the whole kernel.  Teams are not pipelined
 // internally; three teams per SM overlap each other's phases.
 #include "common.cuh"
+#define Y3_FILE_ID 3
 #include "ptx.cuh"
 
 #include <cuda.h>
@@ -543,3 +544,6 @@ int y3_conv_chain_res64(const y3_chain_desc* d, const void* x, const void* w1, c
 }
 
 }  // extern "C"
+
+// y3_debug_set_trap_record (api.cu): this translation unit's copy of the watchdog record pointer
+namespace y3 { cudaError_t conv_chain_set_trap_record(unsigned long long* host_mapped) { return ptx::set_trap_record_tu(host_mapped); } }

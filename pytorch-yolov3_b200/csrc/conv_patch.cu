@@ -29,6 +29,7 @@
 // Cost: (W + 2) / W more MMA rows plus the ragged last tile of every image; the dispatcher
 // (conv_umma.cu) only sends layers here whose tiles are >= 93 % full (W >= 38 at these sizes).
 #include "common.cuh"
+#define Y3_FILE_ID 2
 #include "ptx.cuh"
 
 #include <cuda.h>
@@ -562,3 +563,6 @@ int conv3x3_patch_try(const y3_conv_desc* d, const void* x, const void* w, const
 }
 
 }  // namespace y3
+
+// y3_debug_set_trap_record (api.cu): this translation unit's copy of the watchdog record pointer
+namespace y3 { cudaError_t conv_patch_set_trap_record(unsigned long long* host_mapped) { return ptx::set_trap_record_tu(host_mapped); } }

@@ -27,6 +27,7 @@
 // depend on the previous layer: the producer requests the first ring pass of B tiles BEFORE the
 // programmatic-dependent-launch wait, so they stream in while the previous kernel drains.
 #include "common.cuh"
+#define Y3_FILE_ID 1
 #include "ptx.cuh"
 #include "decode_math.cuh"
 
@@ -993,3 +994,6 @@ extern "C" int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w, co
                          const void* residual, void* y, void* stream) {
   return y3::conv2d_impl(d, x, w, bias, residual, y, stream, d ? (d->flags & 1) : 0);
 }
+
+// y3_debug_set_trap_record (api.cu): this translation unit's copy of the watchdog record pointer
+namespace y3 { cudaError_t conv_umma_set_trap_record(unsigned long long* host_mapped) { return ptx::set_trap_record_tu(host_mapped); } }

@@ -56,15 +56,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Blocking wait with a watchdog: a protocol bug traps (-> CUDA error on the
 // host) instead of hanging the GPU box.  ~8 s at 2 GHz before giving up (far beyond any
-// legitimate stall: a whole 64-image step takes 4 ms).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// legitimate stall: a whole 64-image step takes 4 ms).  Before trapping, the waiting thread leaves a
+// record (source file id / line of the wait, block, thread, barrier, parity) in the host-mapped buffer
+// registered through y3_debug_set_trap_record, if any: the context is dead after the trap, the host
+// memory is not.
+#ifndef Y3_FILE_ID
+#define Y3_FILE_ID 0
+#endif
+static __device__ unsigned long long* g_trap_rec = nullptr;  // one copy per translation unit
+static inline cudaError_t set_trap_record_tu(unsigned long long* host_mapped) {
+  return cudaMemcpyToSymbol(g_trap_rec, &host_mapped, sizeof(host_mapped));
+}
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int line) {
+  unsigned long long* rec = g_trap_rec;
+  if (rec) {
+    rec[1] = ((unsigned long long)Y3_FILE_ID << 32) | (unsigned)line;
+    rec[2] = ((unsigned long long)threadIdx.x << 32) | blockIdx.x;
+    rec[3] = ((unsigned long long)parity << 32) | bar;
+    rec[4] = ((unsigned long long)blockDim.x << 32) | gridDim.x;
+    rec[0] = 0x59335452415021ull;  // "Y3TRAP!"
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar, uint32_t parity, int line) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   uint32_t it = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++it) & 0x3FFu) == 0 && clock64() - t0 > 16000000000ll) __trap();
+    if (((++it) & 0x3FFu) == 0 && clock64() - t0 > 16000000000ll) mbar_timeout(bar, parity, line);
   }
 }
+#define mbar_wait(bar, parity) mbar_wait_at(bar, parity, __LINE__)
 
 // ---- TMA --------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {

@@ -23,7 +23,7 @@ EXPORTS = (
     "y3_stage_images", "y3_conv2d", "y3_conv2d_yolo_head", "y3_conv_chain_stem_u8", "y3_conv_chain_res64", "y3_maxpool", "y3_spp3", "y3_add", "y3_copy_channels", "y3_upsample2x",
     "y3_pack_nchw_f32", "y3_pack_bgr_u8", "y3_im2col3x3_nchw_f32", "y3_im2col3x3_bgr_u8", "y3_yolo_decode_dense", "y3_yolo_decode_cands",
     "y3_nms_workspace_bytes", "y3_nms", "y3_plan_destinations", "y3_compact_kept", "y3_emit_detections",
-    "y3_debug_conv_trace",
+    "y3_debug_conv_trace", "y3_debug_set_trap_record",
 )
 
 ABI_VERSION = 6
@@ -98,6 +98,7 @@ def lib():
                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     L.y3_plan_destinations.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     L.y3_debug_conv_trace.argtypes = [c_void_p, ctypes.c_int]
+    L.y3_debug_set_trap_record.argtypes = [c_void_p]
     L.y3_emit_detections.argtypes = [c_void_p] * 4 + [c_int32] * 3 + [c_void_p] * 4
     L.y3_compact_kept.argtypes = [c_void_p] * 3 + [c_int32] * 2 + [c_void_p] * 2 + [c_int32, c_void_p]
     if L.y3_abi_version() != ABI_VERSION:
@@ -152,6 +153,32 @@ def reset_launch_count():
 def set_pdl(on):
     """Programmatic dependent launch for subsequent launches / graph captures; returns the previous setting."""
     return bool(lib().y3_set_pdl(1 if on else 0))
+
+
+_trap_records = {}
+
+
+def enable_trap_record(device):
+    """Register a pinned host buffer as the watchdog record of ``device`` (see y3_debug_set_trap_record);
+    returns it (int64 tensor of 8 words; word 0 != 0 after a watchdog trap)."""
+    device = torch.device(device)
+    rec = _trap_records.get(device.index)
+    if rec is None:
+        rec = torch.zeros(8, dtype=torch.int64).pin_memory()
+        with torch.cuda.device(device):
+            _check(lib().y3_debug_set_trap_record(rec.data_ptr()))
+        _trap_records[device.index] = rec
+    return rec
+
+
+def describe_trap_record(rec):
+    """Human-readable form of a watchdog record, or None when no trap was recorded."""
+    w = [int(v) & 0xFFFFFFFFFFFFFFFF for v in rec.tolist()]
+    if w[0] == 0:
+        return None
+    files = {1: "conv_umma.cu", 2: "conv_patch.cu", 3: "conv_chain.cu"}
+    return (f"mbarrier watchdog: {files.get(w[1] >> 32, '?')}:{w[1] & 0xFFFFFFFF} block {w[2] & 0xFFFFFFFF} of "
+            f"{w[4] & 0xFFFFFFFF} thread {w[2] >> 32} of {w[4] >> 32} barrier 0x{w[3] & 0xFFFFFFFF:x} parity {w[3] >> 32}")
 
 
 def stage_images(dst, images, threads):

@@ -22,6 +22,9 @@ import torch
 from . import _lib
 
 _TRACE = os.environ.get("Y3_TRACE", "0") == "1"
+# tools/hang_stress.py: random host delay (ms) after every sub-batch launch of inference(), to sweep the ways
+# the sub-batch graphs can interleave on the GPU
+_JITTER_MS = float(os.environ.get("Y3_STRESS_JITTER_MS", "0"))
 # host threads that stage a batch into pinned memory: the box's cores shared between the ranks of a node
 # (torchrun exports LOCAL_WORLD_SIZE), at most 16 — beyond that the copy is memory-bound
 _STAGE_THREADS = max(2, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
@@ -212,6 +215,9 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
                 eng.launch(key)
                 meta.copy_(eng.meta, non_blocking=True)  # kept per (image, class) + first box per class
             mark(f"launched {lo}:{hi}")
+            if _JITTER_MS:
+                import random
+                time.sleep(random.random() * _JITTER_MS * 1e-3)
         # phase 2: per sub-batch, as soon as its NMS is done: destinations -> emit -> download
         base = 0
         pending = []
