@@ -328,10 +328,12 @@ int y3_compact_kept(const y3_cand* sorted, const uint8_t* keep,
  * device; tools/conv_trace.py).  Not used by the hot path. */
 int y3_debug_conv_trace(unsigned long long* out, int n);
 /* Every blocking mbarrier wait of the convolution kernels has a watchdog (~8 s) that traps instead of
- * hanging the GPU.  Register a HOST-MAPPED (pinned, device-accessible) buffer of >= 5 x 8 bytes on the
- * current device and the trapping thread first leaves there: [0] magic 0x59335452415021, [1] source
- * file id << 32 | line of the wait, [2] threadIdx.x << 32 | blockIdx.x, [3] parity << 32 | barrier
- * address, [4] blockDim.x << 32 | gridDim.x.  NULL unregisters.  The record survives the dead context. */
+ * hanging the GPU.  Register a zeroed HOST-MAPPED (pinned, device-accessible) buffer of 12 x 8 bytes on
+ * the current device and every thread that times out first leaves there: [0] magic 0x59335452415021,
+ * [5] number of timed-out threads, and for the LAST of them [1] source file id << 32 | line of the wait,
+ * [2] threadIdx.x << 32 | blockIdx.x, [3] parity << 32 | barrier address, [4] blockDim.x << 32 |
+ * gridDim.x; [8..11] the same four words for the FIRST one.  NULL unregisters.  The record survives the
+ * dead context. */
 int y3_debug_set_trap_record(void* host_mapped);
 
 #ifdef __cplusplus

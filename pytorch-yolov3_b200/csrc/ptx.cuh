@@ -70,12 +70,18 @@ static inline cudaError_t set_trap_record_tu(unsigned long long* host_mapped) {
 static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int line) {
   unsigned long long* rec = g_trap_rec;
   if (rec) {
-    rec[1] = ((unsigned long long)Y3_FILE_ID << 32) | (unsigned)line;
-    rec[2] = ((unsigned long long)threadIdx.x << 32) | blockIdx.x;
-    rec[3] = ((unsigned long long)parity << 32) | bar;
-    rec[4] = ((unsigned long long)blockDim.x << 32) | gridDim.x;
+    // words 1-4: the LAST thread that timed out; words 8-11: the FIRST one; word 5: how many did
+    const unsigned long long n = atomicAdd_system(rec + 5, 1ull);
+    unsigned long long* r = n == 0 ? rec + 7 : rec;
+    r[1] = ((unsigned long long)Y3_FILE_ID << 32) | (unsigned)line;
+    r[2] = ((unsigned long long)threadIdx.x << 32) | blockIdx.x;
+    r[3] = ((unsigned long long)parity << 32) | bar;
+    r[4] = ((unsigned long long)blockDim.x << 32) | gridDim.x;
     rec[0] = 0x59335452415021ull;  // "Y3TRAP!"
     __threadfence_system();
+    // give the other stuck threads a moment to leave their record before the context dies
+    const long long t0 = clock64();
+    while (clock64() - t0 < 40000000ll) {}
   }
   __trap();
 }

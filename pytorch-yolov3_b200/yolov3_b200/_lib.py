@@ -164,7 +164,7 @@ def enable_trap_record(device):
     device = torch.device(device)
     rec = _trap_records.get(device.index)
     if rec is None:
-        rec = torch.zeros(8, dtype=torch.int64).pin_memory()
+        rec = torch.zeros(12, dtype=torch.int64).pin_memory()
         with torch.cuda.device(device):
             _check(lib().y3_debug_set_trap_record(rec.data_ptr()))
         _trap_records[device.index] = rec
@@ -177,8 +177,11 @@ def describe_trap_record(rec):
     if w[0] == 0:
         return None
     files = {1: "conv_umma.cu", 2: "conv_patch.cu", 3: "conv_chain.cu"}
-    return (f"mbarrier watchdog: {files.get(w[1] >> 32, '?')}:{w[1] & 0xFFFFFFFF} block {w[2] & 0xFFFFFFFF} of "
-            f"{w[4] & 0xFFFFFFFF} thread {w[2] >> 32} of {w[4] >> 32} barrier 0x{w[3] & 0xFFFFFFFF:x} parity {w[3] >> 32}")
+
+    def one(v):
+        return (f"{files.get(v[0] >> 32, '?')}:{v[0] & 0xFFFFFFFF} block {v[1] & 0xFFFFFFFF} of {v[3] & 0xFFFFFFFF} "
+                f"thread {v[1] >> 32} of {v[3] >> 32} barrier 0x{v[2] & 0xFFFFFFFF:x} parity {v[2] >> 32}")
+    return f"mbarrier watchdog: {w[5]} threads timed out; first: {one(w[8:12])}; last: {one(w[1:5])}"
 
 
 def stage_images(dst, images, threads):

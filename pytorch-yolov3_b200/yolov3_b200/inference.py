@@ -164,20 +164,24 @@ def inference(net, images, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, 
 
     # Large batches go through the GPU as a few sub-batches on their own streams and plans: while
     # sub-batch k computes, the host stages and uploads k+1 and finishes k-1 (destinations, emit,
-    # download) — the synchronous call hides most of its own host and PCIe time.  (The sub-batch plans
-    # keep programmatic dependent launch: their kernels are short, and the latency at every kernel
-    # boundary costs more than a parked dependent CTA — measured +5-8 % end to end.)
+    # download) — the synchronous call hides most of its own host and PCIe time.  Plans that run side
+    # by side are captured WITHOUT programmatic dependent launch: with it (+5-8 % on this call) two
+    # concurrently replayed graphs of persistent full-SM kernels deadlock once in a few hundred calls —
+    # every CTA of a dependent kernel parked in griddepcontrol.wait for a predecessor that never
+    # completes (tools/hang_stress.py reproduces it in seconds; a single stream with PDL, and any number
+    # of streams without it, run clean).  DESIGN.md §6.
     spans = _sub_batches(B)
     geom = net.geometry(B, H, W)
     io = geom.get("io")
     if io is None:
         multi = len(spans) > 1
-        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if multi else 0)
+        eng0 = net.engine(spans[0][1] - spans[0][0], H, W, slot=1 if multi else 0, concurrent=multi)
         if eng0.device != dev:
             raise RuntimeError(f"net runs on {eng0.device}, inference(device='{device}') requested")
         with torch.cuda.device(dev):
             C, M = eng0.num_classes, eng0.M
-            engines = [net.engine(hi - lo, H, W, slot=(k + 1) if multi else 0) for k, (lo, hi) in enumerate(spans)]
+            engines = [net.engine(hi - lo, H, W, slot=(k + 1) if multi else 0, concurrent=multi)
+                       for k, (lo, hi) in enumerate(spans)]
             io = {"img": _pinned((B, H, W, 3), torch.uint8), "hw": _pinned((B, 2), torch.int32),
                   "meta": [_pinned((e.meta.numel(),), torch.int32) for e in engines],
                   "dst": [_pinned((hi - lo, C), torch.int32) for lo, hi in spans],
