@@ -1,9 +1,9 @@
 // decode.cu — YOLO head decode (yolov3/darknet.py:48-122, :390-399) and the per-image
 // post-processing of yolov3/inference.py:342-353 + cxywh_to_tlbr (:269-283), fused.
 //
-// One warp decodes one box (image, anchor, row, col): its 5+classes logits are contiguous in
-// the NHWC float32 head tensor, so the warp reads them with coalesced 128-byte requests, finds
-// max/argmax and the softmax denominator with shuffles, and lane 0 finishes the box.
+// A warp decodes 32 consecutive boxes (image, anchor, row, col): a box's 5+classes logits are
+// contiguous in the NHWC float32 head tensor; eight lanes reduce one box (max/argmax and the softmax
+// denominator with shuffles), then lane b finishes box b.
 // All fp32 steps keep the reference's operation order (sigmoid, +offset, /grid; exp, *anchor,
 // /train size, *image size) with explicit round-to-nearest intrinsics so no FMA contraction
 // changes a rounding; only sigmoid/exp themselves may differ from torch's by an ulp.
@@ -12,126 +12,25 @@
 
 namespace y3 {
 
-struct BoxOut {
-  float x, y, w, h, prob;
-  int cls;
-};
+static constexpr int CAND_BOXES = 256;  // boxes per CTA of both decode kernels: 32 per warp
 
-// Whole warp cooperates; result valid in every lane.
-__device__ __forceinline__ BoxOut decode_box(const y3_head_desc& d, const float* __restrict__ logits,
-                                             int img, int a, int row, int col, int lane) {
-  const int fields = 5 + d.num_classes;
-  const float* px = logits + ((long long)(img * d.g_h + row) * d.g_w + col) * d.ld + a * fields;
-  // lanes 0..4 hold tx,ty,tw,th,to from the first request
-  float head = (lane < fields) ? __ldg(px + lane) : 0.f;
-  float best = -INFINITY;
-  int best_idx = 0x7fffffff;
-  for (int f = lane; f < fields; f += 32) {
-    const float v = (f == lane) ? head : __ldg(px + f);
-    if (f >= 5 && (v > best)) { best = v; best_idx = f - 5; }
-  }
-  // warp arg-max (first index wins ties, like torch.max)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-    if (ob > best || (ob == best && oi < best_idx)) { best = ob; best_idx = oi; }
-  }
-  float sum = 0.f;
-  for (int f = lane; f < fields; f += 32) {
-    if (f >= 5) {
-      const float v = (f == lane) ? head : __ldg(px + f);
-      sum += expf(v - best);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-
-  const float tx = __shfl_sync(0xffffffffu, head, 0);
-  const float ty = __shfl_sync(0xffffffffu, head, 1);
-  const float tw = __shfl_sync(0xffffffffu, head, 2);
-  const float th = __shfl_sync(0xffffffffu, head, 3);
-  const float to = __shfl_sync(0xffffffffu, head, 4);
-
-  BoxOut o;
-  o.x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)d.g_w);
-  o.y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)d.g_h);
-  o.w = __fdiv_rn(__fmul_rn(expf(tw), d.anchor_w[a]), d.train_w);
-  o.h = __fdiv_rn(__fmul_rn(expf(th), d.anchor_h[a]), d.train_h);
-  // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)
-  o.prob = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
-  o.cls = best_idx;
-  return o;
-}
-
-__device__ __forceinline__ bool next_box(const y3_head_desc& d, long long wid, int& img, int& a,
-                                         int& row, int& col, int& m) {
-  const int cells = d.g_h * d.g_w;
-  const long long per_img = (long long)d.num_anchors * cells;
-  if (wid >= per_img * d.n) return false;
-  img = (int)(wid / per_img);
-  m = (int)(wid - (long long)img * per_img);  // a*cells + row*g_w + col  (darknet.py:118-120)
-  a = m / cells;
-  const int cell = m - a * cells;
-  row = cell / d.g_w;
-  col = cell - row * d.g_w;
-  return true;
-}
-
-__global__ void __launch_bounds__(256)
-decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, float* __restrict__ bbox,
-                    float* __restrict__ prob, long long* __restrict__ cls) {
-  pdl_enter();
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;; wid += warps) {
-    int img, a, row, col, m;
-    if (!next_box(d, wid, img, a, row, col, m)) break;
-    const BoxOut o = decode_box(d, logits, img, a, row, col, lane);
-    if (lane == 0) {
-      const long long g = (long long)img * d.boxes_per_image + d.box_offset + m;
-      reinterpret_cast<float4*>(bbox)[g] = make_float4(o.x, o.y, o.w, o.h);
-      prob[g] = o.prob;
-      cls[g] = (long long)o.cls;
-    }
-  }
-}
-
-// Fused decode + threshold + pixel scaling + truncation + tl/br + compaction.
-// One CTA owns CAND_BOXES consecutive boxes of ONE image, 32 per warp.  Phase 1 (cooperative):
-// EIGHT lanes share a box, so a warp reduces four boxes at a time: lane `sub` of a group loads
-// fields sub, sub+8, ... (all loads of a box are issued before the first use — up to 11 per lane
-// are kept in registers, enough for 5+80 fields; wider heads re-read the remainder), then max /
-// argmax / softmax denominator are reduced over the 8 lanes with three shuffle steps and the raw
-// fields of box b are parked in lane b.  Phase 2 (lane-parallel): lane b finishes box b (sigmoid,
-// exp, scaling, truncation) — 32 boxes per instruction.  Passing boxes are collected in shared
-// memory; the CTA reserves its output range with a single global atomic (per-box atomics on the
-// per-image counters serialise in L2).
-static constexpr int CAND_BOXES = 256;
+// Phase 1 of both decode kernels (cooperative): a warp owns the 32 consecutive boxes m_warp .. m_warp+31
+// of image `img` (nb of them exist).  EIGHT lanes share a box, so the warp reduces four boxes at a time:
+// lane `sub` of a group loads fields sub, sub+8, ... (all loads of a box are issued before the first use —
+// up to 11 per lane are kept in registers, enough for 5+80 fields; wider heads re-read the remainder),
+// then max / argmax / softmax denominator are reduced over the 8 lanes with three shuffle steps and the
+// raw fields of box b are parked in lane b.
 static constexpr int DEC_CACHED = 11;  // fields cached per lane: 8 * 11 = 88 >= 5 + 80
 
-__global__ void __launch_bounds__(256)
-decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
-                    const y3_thresholds* __restrict__ dyn, const int* __restrict__ orig_hw,
-                    y3_cand* __restrict__ cands, int* __restrict__ counts, int cap) {
-  pdl_enter();
-  if (dyn) prob_thresh = dyn->prob_thresh;  // device-resident thresholds: one graph, any setting
-  __shared__ uint4 s_rec[CAND_BOXES][2];
-  __shared__ int s_count, s_base;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void decode_phase1(const y3_head_desc& d, const float* __restrict__ logits, int img,
+                                              int m_warp, int nb, int lane, float& tx, float& ty, float& tw,
+                                              float& th, float& to, float& sum, int& cls) {
   const int sub = lane & 7, grp = lane >> 3;
-  const int img = blockIdx.y;
   const int cells = d.g_h * d.g_w;
-  const int per_img = d.num_anchors * cells;
   const int fields = 5 + d.num_classes;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-
-  // ---- phase 1: four boxes per warp iteration; box b of this warp ends up in lane b --------
-  const int m_warp = blockIdx.x * CAND_BOXES + warp * 32;
-  float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, to = 0.f, sum = 1.f;
-  int cls = 0;
-  const int nb = min(32, per_img - m_warp);
+  tx = ty = tw = th = to = 0.f;
+  sum = 1.f;
+  cls = 0;
   for (int it = 0; it * 4 < nb; ++it) {
     const int b = it * 4 + grp;
     const bool live = b < nb;
@@ -181,6 +80,77 @@ decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, floa
     if ((lane >> 2) == it) { tx = h0; ty = h1; tw = h2; th = h3; to = h4; sum = ps; cls = pc; }
   }
 
+}
+
+// Dense outputs of Darknet.forward (darknet.py:401-405).  Same two phases as decode_cands_kernel: the
+// warp reduces its 32 boxes cooperatively (all loads of four boxes in flight at once), then lane b
+// finishes box b, so the three output arrays are written with coalesced 512 / 128 / 256-byte requests.
+__global__ void __launch_bounds__(256)
+decode_dense_kernel(const y3_head_desc d, const float* __restrict__ logits, float* __restrict__ bbox,
+                    float* __restrict__ prob, long long* __restrict__ cls_out) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int img = blockIdx.y;
+  const int cells = d.g_h * d.g_w;
+  const int per_img = d.num_anchors * cells;
+  const int m_warp = blockIdx.x * CAND_BOXES + warp * 32;
+  const int nb = min(32, per_img - m_warp);
+  if (nb <= 0) return;
+  float tx, ty, tw, th, to, sum;
+  int cls;
+  decode_phase1(d, logits, img, m_warp, nb, lane, tx, ty, tw, th, to, sum, cls);
+  if (lane < nb) {
+    const int m = m_warp + lane;  // a*cells + row*g_w + col  (darknet.py:118-120)
+    const int a = m / cells;
+    const int cell = m - a * cells;
+    const int row = cell / d.g_w;
+    const int col = cell - row * d.g_w;
+    const float x = __fdiv_rn(__fadd_rn(sigmoidf_ref(tx), (float)col), (float)d.g_w);
+    const float y = __fdiv_rn(__fadd_rn(sigmoidf_ref(ty), (float)row), (float)d.g_h);
+    const float w = __fdiv_rn(__fmul_rn(expf(tw), d.anchor_w[a]), d.train_w);
+    const float h = __fdiv_rn(__fmul_rn(expf(th), d.anchor_h[a]), d.train_h);
+    // softmax value of the arg-max class is exp(0)/sum; then * sigmoid(objectness)  (darknet.py:104-108)
+    const float pr = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoidf_ref(to));
+    const long long g = (long long)img * d.boxes_per_image + d.box_offset + m;
+    reinterpret_cast<float4*>(bbox)[g] = make_float4(x, y, w, h);
+    prob[g] = pr;
+    cls_out[g] = (long long)cls;
+  }
+}
+
+// Fused decode + threshold + pixel scaling + truncation + tl/br + compaction.
+// One CTA owns CAND_BOXES consecutive boxes of ONE image, 32 per warp.  Phase 1 (cooperative):
+// EIGHT lanes share a box, so a warp reduces four boxes at a time: lane `sub` of a group loads
+// fields sub, sub+8, ... (all loads of a box are issued before the first use — up to 11 per lane
+// are kept in registers, enough for 5+80 fields; wider heads re-read the remainder), then max /
+// argmax / softmax denominator are reduced over the 8 lanes with three shuffle steps and the raw
+// fields of box b are parked in lane b.  Phase 2 (lane-parallel): lane b finishes box b (sigmoid,
+// exp, scaling, truncation) — 32 boxes per instruction.  Passing boxes are collected in shared
+// memory; the CTA reserves its output range with a single global atomic (per-box atomics on the
+// per-image counters serialise in L2).
+
+__global__ void __launch_bounds__(256)
+decode_cands_kernel(const y3_head_desc d, const float* __restrict__ logits, float prob_thresh,
+                    const y3_thresholds* __restrict__ dyn, const int* __restrict__ orig_hw,
+                    y3_cand* __restrict__ cands, int* __restrict__ counts, int cap) {
+  pdl_enter();
+  if (dyn) prob_thresh = dyn->prob_thresh;  // device-resident thresholds: one graph, any setting
+  __shared__ uint4 s_rec[CAND_BOXES][2];
+  __shared__ int s_count, s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int img = blockIdx.y;
+  const int cells = d.g_h * d.g_w;
+  const int per_img = d.num_anchors * cells;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+
+  // ---- phase 1 (cooperative): box b of this warp's 32 ends up in lane b --------------------------
+  const int m_warp = blockIdx.x * CAND_BOXES + warp * 32;
+  float tx, ty, tw, th, to, sum;
+  int cls;
+  const int nb = min(32, per_img - m_warp);
+  decode_phase1(d, logits, img, m_warp, nb, lane, tx, ty, tw, th, to, sum, cls);
+
   // ---- phase 2: lane b finishes box b ---------------------------------------------------------
   if (lane < nb) {
     const int m = m_warp + lane;
@@ -224,14 +194,6 @@ static int check_head(const y3_head_desc* d, const float* logits) {
   return Y3_OK;
 }
 
-static int decode_grid(const y3_head_desc* d) {
-  const long long boxes = (long long)d->n * d->num_anchors * d->g_h * d->g_w;
-  long long blocks = (boxes + 7) / 8;  // 8 warps per 256-thread CTA
-  const long long cap = (long long)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  return (int)(blocks < 1 ? 1 : blocks);
-}
-
 }  // namespace y3
 
 using namespace y3;
@@ -244,8 +206,10 @@ int y3_yolo_decode_dense(const y3_head_desc* d, const float* logits, float* bbox
   if (rc != Y3_OK) return rc;
   Y3_CHECK_ARG(bbox_xywh && class_prob && class_idx, "decode_dense: null output");
   Y3_CHECK_ARG((reinterpret_cast<uintptr_t>(bbox_xywh) & 15) == 0, "decode_dense: bbox must be 16-byte aligned");
-  Y3_CUDA_OK(launch_kernel(decode_dense_kernel, dim3(decode_grid(d)), dim3(256), 0, (cudaStream_t)stream, 
-      *d, logits, bbox_xywh, class_prob, reinterpret_cast<long long*>(class_idx)));
+  const int per_img = d->num_anchors * d->g_h * d->g_w;
+  Y3_CUDA_OK(launch_kernel(decode_dense_kernel, dim3((per_img + CAND_BOXES - 1) / CAND_BOXES, d->n), dim3(256), 0,
+                           (cudaStream_t)stream, *d, logits, bbox_xywh, class_prob,
+                           reinterpret_cast<long long*>(class_idx)));
   Y3_LAUNCH_OK("decode_dense_kernel");
   return Y3_OK;
 }

@@ -91,6 +91,57 @@ __global__ void spp3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
   }
 }
 
+// The same three pools for feature maps that fit in shared memory (every SPP block in practice:
+// 13x13 at 416, 19x19 at 608): one CTA per (image, group of CVB channel vectors) reads its slice of the
+// map ONCE, and since one-sided windows compose — [h, h+5) of [h', h'+5) is [h, h+9), zero padding
+// included — y9 = pool5(y5) and y13 = pool5(y9), each pool5 a separable row pass + column pass in
+// shared memory.  HBM traffic = the algorithmic 1 read + 3 writes (spp3_kernel re-reads every tap from
+// L2: 169 loads per output).
+template <int CVB>
+__global__ void __launch_bounds__(256)
+spp3_tile_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y5,
+                 __nv_bfloat16* __restrict__ y9, __nv_bfloat16* __restrict__ y13, int h, int w, int cvec,
+                 int ld_x, int ld_y) {
+  pdl_enter();
+  extern __shared__ uint4 spp_smem[];
+  const int hw = h * w, total = hw * CVB;
+  uint4* const S = spp_smem;
+  uint4* const T = spp_smem + total;
+  const int groups = cvec / CVB;
+  const int img = blockIdx.x / groups;
+  const int c0 = (blockIdx.x - img * groups) * CVB * 8;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const __nv_bfloat16* const xin = x + (long long)img * hw * ld_x + c0;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int p = e / CVB, cv = e - p * CVB;
+    S[e] = ld_nc_16(xin + (long long)p * ld_x + cv * 8);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int stage = 0; stage < 3; ++stage) {
+    __nv_bfloat16* const out = (stage == 0 ? y5 : stage == 1 ? y9 : y13) + (long long)img * hw * ld_y + c0;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {  // row pass: [w, w+5), zeros right of the map
+      const int p = e / CVB;
+      const int lim = min(5, w - (p % w));
+      uint4 m = S[e];
+      for (int d = 1; d < lim; ++d) m = bf16x8_max(m, S[e + d * CVB]);
+      if (lim < 5) m = bf16x8_max(m, zero);
+      T[e] = m;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {  // column pass: [h, h+5), zeros below the map
+      const int p = e / CVB, cv = e - p * CVB;
+      const int lim = min(5, h - p / w);
+      uint4 m = T[e];
+      for (int d = 1; d < lim; ++d) m = bf16x8_max(m, T[e + d * w * CVB]);
+      if (lim < 5) m = bf16x8_max(m, zero);
+      S[e] = m;  // input of the next, wider pool
+      st_16(out + (long long)p * ld_y + cv * 8, m);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- shortcut add (yolov3/darknet.py:376-379), unfused form ------------------------------
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ y, long long pixels, int cvec, int ld_a,
@@ -283,6 +334,19 @@ int y3_spp3(const void* x, void* y5, void* y9, void* y13, int32_t n, int32_t h, 
   Y3_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "spp3: bad shape");
   Y3_CHECK_ARG(ld_x >= c && ld_y >= c && ld_x % 8 == 0 && ld_y % 8 == 0, "spp3: bad pitch");
   Y3_CHECK_ARG(aligned16(x) && aligned16(y5) && aligned16(y9) && aligned16(y13), "spp3: alignment");
+  constexpr int CVB = 4;  // 64 channels per CTA: 2 x (h*w*64 B) of shared memory
+  const size_t smem = 2 * (size_t)h * w * CVB * sizeof(uint4);
+  if ((c / 8) % CVB == 0 && smem <= 200 * 1024 && (long long)n * (c / 8 / CVB) < (1ll << 31)) {
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      Y3_CUDA_OK(cudaFuncSetAttribute(spp3_tile_kernel<CVB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      smem_set = 200 * 1024;
+    }
+    Y3_CUDA_OK(launch_kernel(spp3_tile_kernel<CVB>, dim3(n * (c / 8 / CVB)), dim3(256), smem, (cudaStream_t)stream,
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y5, (__nv_bfloat16*)y9, (__nv_bfloat16*)y13, h, w, c / 8, ld_x, ld_y));
+    Y3_LAUNCH_OK("spp3_tile_kernel");
+    return Y3_OK;
+  }
   const long long work = (long long)n * h * w * (c / 8);
   Y3_CUDA_OK(launch_kernel(spp3_kernel, dim3(grid_for(work, 128)), dim3(128), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y5, (__nv_bfloat16*)y9, (__nv_bfloat16*)y13, n, h, w, c / 8, ld_x, ld_y));

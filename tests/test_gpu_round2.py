@@ -382,3 +382,18 @@ def test_cli_reference_main_unmodified_on_rebound_hot_path(tiny_on_disk, tmp_pat
         want = yolov3_b200.inference(net, img, device="cuda:0", prob_thresh=0.2, nms_iou_thresh=0.3)[0]
         assert np.array_equal(np.asarray(drawn["bbox"]).reshape(-1, 4), want[0])
         assert np.array_equal(np.asarray(drawn["cls"], dtype=np.int64), want[2])
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 32, 19, 19), (3, 512, 13, 13), (1, 8, 19, 19), (2, 64, 7, 23), (1, 64, 3, 4)])
+def test_spp3_tile_and_fallback_kernels_equal_three_pools(n, c, h, w):
+    """y3_spp3: the shared-memory separable kernel (channel groups of 64) and the generic fallback
+    (other channel counts) against the reference's three patched max-pools, exact."""
+    g = torch.Generator().manual_seed(h * 100 + w)
+    x = (torch.randn(n, c, h, w, generator=g) - 0.3).bfloat16()
+    xin = x.permute(0, 2, 3, 1).contiguous().cuda()
+    outs = [torch.zeros_like(xin) for _ in range(3)]
+    _lib.spp3(xin.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), n, h, w, c, c, c)
+    torch.cuda.synchronize()
+    for o, k in zip(outs, (5, 9, 13)):
+        ref = DO.maxpool_block(x.float(), {"size": k, "stride": 1})
+        assert torch.equal(o.float().cpu().permute(0, 3, 1, 2), ref), k
