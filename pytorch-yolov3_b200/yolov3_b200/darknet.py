@@ -289,11 +289,15 @@ class Darknet(torch.nn.Module):
         gives further independent instances (own buffers and graphs) of the same geometry:
         ``inference`` pipelines sub-batches through several of them.  ``concurrent`` (honoured when
         the plan is first built) marks a plan that runs next to others on different streams: its
-        graphs are captured without programmatic dependent launch (see ``y3_set_pdl``)."""
+        graphs are captured without programmatic dependent launch (see ``y3_set_pdl``).  Activation
+        buffers are recycled along the network (liveness-based); set ``net.keep_activations = True``
+        before the plan is built to give every block output its own buffer (debugging / tests that read
+        intermediate tensors through ``engine.views``)."""
         geom = self.geometry(batch, height, width)
         eng = geom["engines"].get(slot)
         if eng is None:
-            eng = Engine(self, batch, height, width, self._target_device(), pdl=not concurrent)
+            eng = Engine(self, batch, height, width, self._target_device(), pdl=not concurrent,
+                         alias=not getattr(self, "keep_activations", False))
             geom["engines"][slot] = eng
         return eng
 

@@ -42,8 +42,11 @@ class View:
 
 
 class Engine:
-    def __init__(self, net, batch, height, width, device, pdl=True):
+    def __init__(self, net, batch, height, width, device, pdl=True, alias=True):
         self.net, self.B, self.H, self.W, self.device = net, batch, height, width, device
+        # liveness-based reuse of activation memory (off: every block output keeps its own buffer, which
+        # the teacher-forced tests need to read intermediate tensors back after a run)
+        self.alias = alias and os.environ.get("Y3_NO_ALIAS", "0") != "1"
         # programmatic dependent launch in this plan's graphs (off for plans that run concurrently)
         self.pdl = pdl and os.environ.get("Y3_NO_PDL", "0") != "1"
         self.use_graphs = os.environ.get("Y3_NO_GRAPH", "0") != "1"
@@ -160,7 +163,7 @@ class Engine:
                 C, H, W = shape[i]
                 if C % 8:
                     raise NotImplementedError(f"block {i}: concat of {C} channels (multiple of 8 required)")
-                concat_buf[i] = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+                concat_buf[i] = None  # allocated from the pool when its first producer runs (concat_of)
                 off = 0
                 for j in b["layers"]:
                     r = root(j)
@@ -173,17 +176,62 @@ class Engine:
         views = {}
         self._keep = []  # buffers kept alive
 
+        # ---- activation memory: a pool of buffers reused once their last reader has been emitted --------
+        # Kernels run in emission order on one stream (every kernel waits for its predecessors before it
+        # touches activations, also under programmatic dependent launch), so a buffer whose last consumer
+        # sits at an EARLIER block index than the producer being emitted can be handed out again.  Best fit
+        # over the free buffers, a new one when none is large enough: Darknet's tensors shrink with depth,
+        # so the few large early buffers serve the whole network (5.2 GB -> ~1 GB at batch 64, 416x416).
+        FOREVER = 1 << 30
+        pool = []  # [uint8 tensor, free?, last consumer block]
+        self.activation_bytes_unaliased = 0
+
+        def last_reader(j):
+            return max(consumers.get(j, [FOREVER]))
+
+        def pool_get(nbytes, last):
+            nbytes = _ceil(nbytes, 1024)
+            self.activation_bytes_unaliased += nbytes
+            best = None
+            if self.alias and last < FOREVER:
+                for e in pool:
+                    if e[1] and e[0].numel() >= nbytes and (best is None or e[0].numel() < best[0].numel()):
+                        best = e
+            if best is None:
+                best = [torch.empty(nbytes, device=dev, dtype=torch.uint8), False, last]
+                pool.append(best)
+            best[1], best[2] = False, last
+            return best[0]
+
+        def pool_release(i):
+            if self.alias:
+                for e in pool:
+                    if not e[1] and e[2] < i:
+                        e[1] = True
+
+        def typed(raw, dims, dtype):
+            n = 1
+            for d_ in dims:
+                n *= d_
+            return raw[:n * (4 if dtype == torch.float32 else 2)].view(dtype).view(*dims)
+
+        def concat_of(r):
+            if concat_buf[r] is None:
+                C, H, W = shape[r]
+                concat_buf[r] = typed(pool_get(B * H * W * C * 2, last_reader(r)), (B, H, W, C), torch.bfloat16)
+            return concat_buf[r]
+
         def alloc(i, f32=False, c_store=None):
             C, H, W = shape[i]
             if i in placement and not f32:
                 r, off = placement[i]
-                buf = concat_buf[r]
+                buf = concat_of(r)
                 return View(buf, _p(buf) + off * 2, C, buf.shape[3], H, W)
             cs = c_store or C
-            buf = torch.empty(B, H, W, cs, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-            if cs != C:
-                buf.zero_()
-            self._keep.append(buf)
+            dtype = torch.float32 if f32 else torch.bfloat16
+            # YOLO head logits are read by the decode kernels AFTER the whole backbone: never recycled
+            last = FOREVER if f32 else last_reader(i)
+            buf = typed(pool_get(B * H * W * cs * (4 if f32 else 2), last), (B, H, W, cs), dtype)
             return View(buf, _p(buf), cs, cs, H, W, f32)
 
         # network input.  A first layer that is 3x3/s1/pad1 over <= 3 channels (every shipped cfg)
@@ -252,6 +300,7 @@ class Engine:
             t = b["type"]
             if i in done or i in fused_blocks:
                 continue
+            pool_release(i)
             if t == "convolutional" and res_chain_at(i):
                 xin = views[inputs_of(i)[0]]
                 tgt = fused_into[i + 1]
@@ -390,7 +439,7 @@ class Engine:
                 if len(b["layers"]) == 1:
                     views[i] = views[root(i)]
                     continue
-                buf = concat_buf[i]
+                buf = concat_of(i)
                 off = 0
                 for j in b["layers"]:
                     r = root(j)
@@ -406,6 +455,8 @@ class Engine:
             elif t == "yolo":
                 views[i] = views[root(i)]
         self.views = views
+        self._keep = [e[0] for e in pool]
+        self.activation_bytes = sum(e[0].numel() for e in pool)
         self.backbone_ops = ops
         self.num_fused = {"shortcut": len(residual_of), "upsample": len(fused_into) - len(residual_of),
                           "concat_slices": len(placement)}

@@ -299,6 +299,7 @@ def test_nms_edge_cases():
 @pytest.fixture(scope="module")
 def micro():
     net = yolov3_b200.Darknet(os.path.join(GOLDEN, "micro.cfg"), device="cuda:0")
+    net.keep_activations = True  # these tests read intermediate tensors back through engine.views
     return net.load_weights(os.path.join(GOLDEN, "micro.weights")).eval()
 
 
@@ -469,7 +470,9 @@ def test_inference_argument_semantics(micro):
 # ------------------------------------------------------------------------------------------
 # full-size networks with calibrated synthetic weights
 # ------------------------------------------------------------------------------------------
-def build_full(name, size, tmp_path_factory):
+def build_full(name, size, tmp_path_factory, keep_activations=True):
+    """keep_activations: every block output keeps its own buffer (the teacher-forced checks read them
+    back); False = the production plan, activation buffers recycled along the network."""
     cfg = os.path.join(MODELS, name + ".cfg")
     blocks, net_info = DO.load_model(cfg)
     with torch.no_grad():
@@ -477,6 +480,7 @@ def build_full(name, size, tmp_path_factory):
     wpath = str(tmp_path_factory.mktemp("w") / (name + ".weights"))
     DO.write_weights(wpath, params, blocks, net_info)
     net = yolov3_b200.Darknet(cfg, device="cuda:0").load_weights(wpath).eval()
+    net.keep_activations = keep_activations
     return net, blocks, net_info, params
 
 

@@ -36,7 +36,7 @@ def record_parity(key, value):
 
 @pytest.fixture(scope="module")
 def yolov3_full(tmp_path_factory):
-    return build_full("yolov3", 416, tmp_path_factory)
+    return build_full("yolov3", 416, tmp_path_factory, keep_activations=False)  # production plans (recycled buffers)
 
 
 @pytest.fixture(scope="module")
@@ -326,7 +326,7 @@ def test_nccl_detection_gather_content_two_ranks(tmp_path):
 @pytest.fixture(scope="module")
 def tiny_on_disk(tmp_path_factory):
     import cv2
-    net, blocks, net_info, params = build_full("yolov3-tiny", 416, tmp_path_factory)
+    net, blocks, net_info, params = build_full("yolov3-tiny", 416, tmp_path_factory, keep_activations=False)
     d = tmp_path_factory.mktemp("imgs")
     rng = np.random.default_rng(11)
     shapes = [(416, 416), (375, 500), (480, 640), (416, 416), (300, 300), (427, 640), (416, 416)]
@@ -397,3 +397,23 @@ def test_spp3_tile_and_fallback_kernels_equal_three_pools(n, c, h, w):
     for o, k in zip(outs, (5, 9, 13)):
         ref = DO.maxpool_block(x.float(), {"size": k, "stride": 1})
         assert torch.equal(o.float().cpu().permute(0, 3, 1, 2), ref), k
+
+
+@pytest.mark.parametrize("name,size,batch", [("yolov3", 416, 8), ("yolov3-spp", 608, 2), ("yolov3-tiny", 416, 5)])
+def test_recycled_activation_buffers_change_nothing(name, size, batch, tmp_path_factory):
+    """Liveness-based reuse of activation memory (engine.py pool): identical detections and identical dense
+    outputs to a plan where every block output keeps its own buffer; several times less memory."""
+    kept = build_full(name, size, tmp_path_factory, keep_activations=True)[0]
+    lean = build_full(name, size, tmp_path_factory, keep_activations=False)[0]
+    rng = np.random.default_rng(size + batch)
+    imgs = [rng.integers(0, 256, (size, size, 3), dtype=np.uint8) for _ in range(batch)]
+    a = yolov3_b200.inference(kept, imgs, device="cuda:0", prob_thresh=0.05, resize=False)
+    b = yolov3_b200.inference(lean, imgs, device="cuda:0", prob_thresh=0.05, resize=False)
+    assert same_results(a, b) and sum(len(r[1]) for r in a) > 100
+    x = torch.rand(2, 3, size, size, generator=torch.Generator().manual_seed(5)).cuda()
+    fa, fb = kept.forward(x), lean.forward(x)
+    assert all(torch.equal(fa[k], fb[k]) for k in fa)
+    ea, eb = kept.engine(2, size, size), lean.engine(2, size, size)
+    assert ea.alias is False and eb.alias is True
+    assert eb.activation_bytes * 2 < ea.activation_bytes
+    print(f"{name}@{size} B=2: {eb.activation_bytes / 2**20:.0f} MiB recycled vs {ea.activation_bytes / 2**20:.0f} MiB")
