@@ -99,7 +99,10 @@ typedef struct y3_conv_desc {
                                through the im2col tensor map even for 1x1/s1;
                                bit1: use the direct (register->global)
                                epilogue instead of the staged TMA-store one;
-                               bit2: never use CTA-pair (cta_group::2) tiles */
+                               bit2: never use CTA-pair (cta_group::2) tiles;
+                               bit3: stream the weights through the operand
+                               ring even where the layer's whole slab could
+                               stay resident in shared memory */
 } y3_conv_desc;
 
 int y3_conv2d(const y3_conv_desc* d, const void* x, const void* w,

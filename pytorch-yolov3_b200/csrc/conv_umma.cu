@@ -157,7 +157,11 @@ __device__ __forceinline__ void emit_cand(const ConvKernelParams& p, int a, bool
 // 256-row tile — each CTA stages its own 128 rows of A and HALF of the weight slab, the leader's
 // MMAs read both halves, so per-SM operand traffic and smem per stage drop by a third and the
 // pipeline gets deep enough to cover L2/HBM latency at full tensor rate.
-template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG>
+// RES_KB > 0: the layer's whole weight slab (RES_KB k-blocks of this CTA's rows; one n tile per layer) is
+// loaded ONCE per CTA and stays resident in shared memory; the ring then carries A only.  For layers with
+// few k-blocks (1x1 over <= 256 channels, 3x3 over 64) the per-tile weight re-load is a third to a half of
+// the L2 -> SM traffic that bounds them.
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, int RES_KB = 0>
 struct ConvCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_ROWS = BLOCK_N / CG;  // weight rows staged by THIS CTA
@@ -165,7 +169,8 @@ struct ConvCfg {
   // keep every stage 1024B-aligned (required for SWIZZLE_128B, harmless otherwise)
   static constexpr int A_STRIDE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_STRIDE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = A_STRIDE + B_STRIDE;
+  static constexpr int STAGE_BYTES = RES_KB > 0 ? A_STRIDE : A_STRIDE + B_STRIDE;
+  static constexpr int RES_BYTES = RES_KB * B_STRIDE;  // resident weights, after the ring
   // epilogue staging: 128 rows x BLOCK_N bf16, in column blocks of one swizzle span each
   static constexpr int EPI_SPAN = BLOCK_N * 2 >= 128 ? 128 : BLOCK_N * 2;  // bytes per staged row
   static constexpr int EPI_COLS = EPI_SPAN / 2;                            // columns per block
@@ -182,13 +187,13 @@ struct ConvCfg {
   static constexpr int BAR_BYTES = 512;
   // dynamic smem is declared __align__(1024): no alignment slack needed
   static constexpr int SMEM_LIMIT = 232448 - BAR_BYTES - BIAS_BYTES;
-  static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;
-  static constexpr int MAX_STAGES = 16;  // barrier block: (2*STAGES + 13) * 8 + 8 bytes <= 512
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - STAGING_BYTES - RES_BYTES) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = 16;  // barrier block: (2*STAGES + 14) * 8 + 8 bytes <= 512
   static constexpr int STAGES = STAGES_RAW > MAX_STAGES ? MAX_STAGES : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int TMEM_COLS_RAW = 2 * BLOCK_N;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64
                                  : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + STAGING_BYTES + BAR_BYTES + BIAS_BYTES;
   // UMMA smem descriptor pieces (K-major, swizzle span = BLOCK_K*2 bytes)
   static constexpr uint64_t LAYOUT_TYPE = BLOCK_K == 64 ? 2 : BLOCK_K == 32 ? 4 : 6;
   static constexpr uint64_t SBO = 8 * BLOCK_K * 2;  // 8 rows of one swizzle atom
@@ -215,12 +220,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t 
   return desc_hi | (1ull << 16) | uint64_t((smem_addr >> 4) & 0x3FFFu);
 }
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false>
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false, int RES_KB = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG, RES_KB>;
   constexpr int STAGES = Cfg::STAGES;
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   const int tile_first = blockIdx.x / CG;   // persistent loop over tiles, one CTA (pair) per SM (pair)
@@ -229,7 +234,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();  // the swizzled operand tiles need 1024-byte alignment
-  const uint32_t staging_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024B-aligned
+  const uint32_t wres_base = smem_base + STAGES * Cfg::STAGE_BYTES;      // resident weights (RES_KB > 0), 1024B-aligned
+  const uint32_t staging_base = wres_base + Cfg::RES_BYTES;              // 1024B-aligned
   const uint32_t bar_base = staging_base + Cfg::STAGING_BYTES;
   // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], res[8], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -238,6 +244,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto res_bar = [&](int q) { return bar_base + 8u * (2 * STAGES + 4 + q); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 12);
+  const uint32_t wres_bar = bar_base + 8u * (2 * STAGES + 13);           // resident weights landed
   uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_ptr_addr - smem_base));
   const uint32_t bias_base = bar_base + Cfg::BAR_BYTES;  // float [2][BLOCK_N]
 
@@ -268,6 +275,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_init(tempty_bar(a), 4 * split * CG);  // one arrival per working epilogue warp (of both CTAs)
     }
     for (int q = 0; q < 8; ++q) ptx::mbar_init(res_bar(q), 1);
+    if (RES_KB > 0) ptx::mbar_init(wres_bar, CG);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -288,6 +296,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== TMA producer =====================
     // One thread, and its instruction stream is on the critical path of every ring refill (a few
     // extra instructions per k-block cost 3-6 % on the deep layers — measured): keep the loop minimal.
+    if (RES_KB > 0) {
+      // ---- resident weights: every k-block of this CTA's rows once (constants: before the PDL wait),
+      // then a ring of A tiles only
+      if (lane == 0) {
+        const uint32_t full_base = CG == 2 ? ptx::mapa(full_bar(0), 0) : full_bar(0);
+        if (tile_first < num_tiles) {
+          const uint32_t wbar = CG == 2 ? ptx::mapa(wres_bar, 0) : wres_bar;
+          if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(wres_bar, CG * RES_KB * Cfg::B_BYTES);
+          else ptx::mbar_arrive_cluster(wbar);
+          for (int kb = 0; kb < RES_KB; ++kb)
+            ptx::tma_load_2d<CG>(wres_base + kb * Cfg::B_STRIDE, &tmap_b, wbar, kb * BLOCK_K, (int)cta_rank * Cfg::B_ROWS);
+        }
+        pdl_wait();
+        Y3_TRACE(2);
+        uint32_t phase = 0;
+        uint32_t a_dst = smem_base, fbar = full_base, fbar_l = full_bar(0), ebar = empty_bar(0);
+        const uint32_t fbar_end = full_bar(STAGES);
+        const int cin = p.cin_blocks * BLOCK_K;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+          const int m0 = (tile * CG + (int)cta_rank) * BLOCK_M;  // one n tile: tile == m tile
+          const int img = fast_div(m0, p.div_howo);
+          const int rem = m0 - img * p.HoWo;
+          const int ho0 = fast_div(rem, p.div_wo);
+          const int wo0 = rem - ho0 * p.Wo;
+          const int w_base = wo0 * p.stride - p.pad;
+          const int h_base = ho0 * p.stride - p.pad;
+          int r = 0, s = 0, c = 0;
+          for (int kb = 0; kb < RES_KB; ++kb) {
+            ptx::mbar_wait(ebar, phase ^ 1u);
+            if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(fbar_l, CG * Cfg::A_BYTES);
+            else ptx::mbar_arrive_cluster(fbar);
+            if (p.a_tiled) ptx::tma_load_2d<CG>(a_dst, &tmap_a, fbar, c, m0);
+            else ptx::tma_load_im2col_4d<CG>(a_dst, &tmap_a, fbar, c, w_base, h_base, img, (uint16_t)s, (uint16_t)r);
+            c += BLOCK_K;
+            if (c == cin) { c = 0; if (++s == p.S) { s = 0; ++r; } }
+            a_dst += Cfg::STAGE_BYTES; fbar += 8; fbar_l += 8; ebar += 8;
+            if (fbar_l == fbar_end) { a_dst = smem_base; fbar = full_base; fbar_l = full_bar(0); ebar = empty_bar(0); phase ^= 1u; }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       uint32_t phase = 0;
       // CG == 2: TMA completions of BOTH CTAs are counted on the leader's full barrier
@@ -374,8 +423,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t DESC_STEP = Cfg::STAGE_BYTES >> 4;  // smem descriptor address field counts 16-byte units
       const uint64_t desc_a0 = make_smem_desc(smem_base, Cfg::DESC_HI);
-      const uint64_t desc_b0 = make_smem_desc(smem_base + Cfg::A_STRIDE, Cfg::DESC_HI);
+      const uint64_t desc_b0 = make_smem_desc(RES_KB > 0 ? wres_base : smem_base + Cfg::A_STRIDE, Cfg::DESC_HI);
+      constexpr uint32_t RES_STEP = Cfg::B_STRIDE >> 4;
       uint64_t desc_a = desc_a0, desc_b = desc_b0;
+      if (RES_KB > 0 && tile_first < num_tiles) {  // the resident weights (both CTAs' halves) have landed
+        ptx::mbar_wait(wres_bar, 0);
+        ptx::tc_fence_after();
+      }
       uint32_t fbar = full_bar(0), ebar = empty_bar(0);
       const uint32_t fbar_end = full_bar(STAGES);
       uint32_t phase = 0;
@@ -388,6 +442,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         uint32_t accumulate = 0;  // the tile's first MMA overwrites the accumulator
+        if (RES_KB > 0) desc_b = desc_b0;  // k-block 0 of the resident slab
         for (int kb = p.num_kb; kb > 0; --kb) {
           ptx::mbar_wait(fbar, phase);  // TMA bytes have landed
           ptx::tc_fence_after();
@@ -398,9 +453,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             accumulate = 1;
           }
           ptx::umma_commit<CG>(ebar);  // smem stage reusable (in both CTAs) once these MMAs retire
-          fbar += 8; ebar += 8; desc_a += DESC_STEP; desc_b += DESC_STEP;
+          fbar += 8; ebar += 8; desc_a += DESC_STEP; desc_b += RES_KB > 0 ? RES_STEP : DESC_STEP;
           if (fbar == fbar_end) {
-            fbar = full_bar(0); ebar = empty_bar(0); desc_a = desc_a0; desc_b = desc_b0;
+            fbar = full_bar(0); ebar = empty_bar(0); desc_a = desc_a0;
+            if (RES_KB == 0) desc_b = desc_b0;
             phase ^= 1u;
           }
         }
@@ -787,11 +843,12 @@ struct DecodeArgs {
   int cap;
 };
 
-template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false>
+template <int BLOCK_N, int BLOCK_K, bool STAGED, int CG, bool DECODE = false, int RES_KB = 0>
 static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, cudaStream_t stream, int force_im2col,
                        const DecodeArgs* dec = nullptr) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGED, CG, RES_KB>;
+  static_assert(RES_KB == 0 || Cfg::STAGES >= 4, "resident weights leave too few A stages");
   const int ho = (d->h + 2 * d->pad - d->ksize) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->ksize) / d->stride + 1;
   const long long M = (long long)d->n * ho * wo;
@@ -864,7 +921,7 @@ static int launch_conv(const y3_conv_desc* d, const void* x, const void* w, cons
     }
   }
 
-  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED, CG, DECODE>;
+  auto kernel = conv_umma_kernel<BLOCK_N, BLOCK_K, STAGED, CG, DECODE, RES_KB>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     Y3_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -907,11 +964,28 @@ static int dispatch_epi(const y3_conv_desc* d, const void* x, const void* w, con
     return launch_conv<BLOCK_N, BLOCK_K, false, 1>(d, x, w, bias, residual, y, stream, force_im2col);
   // 128- and 256-channel tiles: CTA pairs (cta_group::2) — each CTA stages only half of the weight slab,
   // which is what the L2 -> SM path limits.  flags bit2 forces single-CTA tiles.
+  // layers with ONE n tile and few k-blocks keep their weights resident in shared memory (RES_KB):
+  // 1x1 128->64 (2 k-blocks), 1x1 256->128 (4), 3x3 64->128 (9).  Y3_NO_BRES=1 streams them as before.
+  static int bres = -1;
+  if (bres < 0) { const char* e = getenv("Y3_NO_BRES"); bres = (e && e[0] == '1') ? 0 : 1; }
+  const int num_kb = d->ksize * d->ksize * (d->cin / BLOCK_K);
+  const bool one_n_tile = bres && d->cout == BLOCK_N && !(d->flags & 8);
   if constexpr ((BLOCK_N == 256 || BLOCK_N == 128) && BLOCK_K == 64) {
     const long long M = (long long)d->n * ((d->h + 2 * d->pad - d->ksize) / d->stride + 1) *
                         ((d->w + 2 * d->pad - d->ksize) / d->stride + 1);
-    if (!(d->flags & 4) && M >= 2 * BLOCK_M)
+    if (!(d->flags & 4) && M >= 2 * BLOCK_M) {
+      if constexpr (BLOCK_N == 128) {
+        if (one_n_tile && num_kb == 9)
+          return launch_conv<BLOCK_N, BLOCK_K, true, 2, false, 9>(d, x, w, bias, residual, y, stream, force_im2col);
+        if (one_n_tile && num_kb == 4)
+          return launch_conv<BLOCK_N, BLOCK_K, true, 2, false, 4>(d, x, w, bias, residual, y, stream, force_im2col);
+      }
       return launch_conv<BLOCK_N, BLOCK_K, true, 2>(d, x, w, bias, residual, y, stream, force_im2col);
+    }
+  }
+  if constexpr (BLOCK_N == 64 && BLOCK_K == 64) {
+    if (one_n_tile && num_kb == 2)
+      return launch_conv<BLOCK_N, BLOCK_K, true, 1, false, 2>(d, x, w, bias, residual, y, stream, force_im2col);
   }
   return launch_conv<BLOCK_N, BLOCK_K, true, 1>(d, x, w, bias, residual, y, stream, force_im2col);
 }

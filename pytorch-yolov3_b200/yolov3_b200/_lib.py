@@ -195,10 +195,12 @@ def stage_images(dst, images, threads):
 # ---- kernels --------------------------------------------------------------------------------
 
 def conv2d(x_ptr, w, bias, y_ptr, *, n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, leaky,
-           res_ptr=None, ld_res=0, out_f32=False, upsample2x=False, force_im2col=False, force_direct=False, force_1cta=False):
+           res_ptr=None, ld_res=0, out_f32=False, upsample2x=False, force_im2col=False, force_direct=False, force_1cta=False,
+           force_stream_weights=False):
     """Raw-pointer form used by the engine plan (views into concat buffers are plain pointers)."""
     d = ConvDesc(n, h, w_in, cin, cout, ksize, stride, pad, ld_x, ld_y, ld_res, int(leaky), int(out_f32),
-                 int(upsample2x), (1 if force_im2col else 0) | (2 if force_direct else 0) | (4 if force_1cta else 0))
+                 int(upsample2x), (1 if force_im2col else 0) | (2 if force_direct else 0) | (4 if force_1cta else 0)
+                 | (8 if force_stream_weights else 0))
     _check(lib().y3_conv2d(ctypes.byref(d), x_ptr, _ptr(w), _ptr(bias), res_ptr, y_ptr, _stream()))
 
 

@@ -417,3 +417,42 @@ def test_recycled_activation_buffers_change_nothing(name, size, batch, tmp_path_
     assert ea.alias is False and eb.alias is True
     assert eb.activation_bytes * 2 < ea.activation_bytes
     print(f"{name}@{size} B=2: {eb.activation_bytes / 2**20:.0f} MiB recycled vs {ea.activation_bytes / 2**20:.0f} MiB")
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout,k,stride,res", [
+    (2, 104, 104, 128, 64, 1, 1, False),   # 1x1 128->64: 2 resident k-blocks, single-CTA tiles
+    (3, 52, 52, 256, 128, 1, 1, False),    # 1x1 256->128: 4 resident k-blocks, CTA pairs
+    (2, 104, 104, 64, 128, 3, 1, True),    # 3x3 64->128 + shortcut: 9 resident k-blocks, im2col A
+    (2, 208, 208, 64, 128, 3, 2, False),   # 3x3 / 2 64->128 (block 5 of yolov3)
+    (1, 37, 41, 64, 128, 3, 1, True),      # odd extents, ragged last tile of a pair
+    (1, 5, 7, 128, 64, 1, 1, False),       # fewer tiles than SMs
+])
+def test_conv_resident_weights_equal_streamed_weights_and_oracle(n, H, W, cin, cout, k, stride, res):
+    """conv_umma.cu with the layer's weights resident in shared memory (RES_KB) vs the same kernel streaming
+    them through the ring (flags bit3): same MMAs in the same order -> bit-identical; both within the
+    convolution tolerance of torch fp32 on the bf16 operands."""
+    from test_gpu_parity import CONV_TOL, fold, nhwc_bf16, rel_err
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(H * W + cin + cout + k)
+    pad = (k - 1) // 2
+    x = torch.randn(n, cin, H, W, generator=g)
+    prm = {"weight": torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5,
+           "bias": torch.randn(cout, generator=g) * 0.1}
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = torch.randn(n, cout, Ho, Wo, generator=g)
+    w, b = fold(prm, cin, cout)
+    xb, rb = nhwc_bf16(x), nhwc_bf16(r)
+    outs = []
+    for stream_w in (False, True):
+        buf = torch.zeros(n, Ho, Wo, cout, device=dev(), dtype=torch.bfloat16)
+        _lib.conv2d(xb.data_ptr(), w, b, buf.data_ptr(), n=n, h=H, w_in=W, cin=cin, cout=cout, ksize=k, stride=stride,
+                    pad=pad, ld_x=cin, ld_y=cout, leaky=True, res_ptr=rb.data_ptr() if res else None,
+                    ld_res=cout if res else 0, force_stream_weights=stream_w)
+        torch.cuda.synchronize()
+        outs.append(buf.float().cpu())
+    assert torch.equal(outs[0], outs[1])
+    ref = F.leaky_relu(F.conv2d(xb.float().cpu().permute(0, 3, 1, 2), prm["weight"].bfloat16().float(), prm["bias"],
+                                stride=stride, padding=pad), 0.1)
+    if res:
+        ref = ref + rb.float().cpu().permute(0, 3, 1, 2)
+    assert rel_err(outs[0].permute(0, 3, 1, 2), ref) <= CONV_TOL
