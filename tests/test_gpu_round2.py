@@ -415,7 +415,7 @@ def test_recycled_activation_buffers_change_nothing(name, size, batch, tmp_path_
     assert all(torch.equal(fa[k], fb[k]) for k in fa)
     ea, eb = kept.engine(2, size, size), lean.engine(2, size, size)
     assert ea.alias is False and eb.alias is True
-    assert eb.activation_bytes * 2 < ea.activation_bytes
+    assert eb.activation_bytes < 0.7 * ea.activation_bytes
     print(f"{name}@{size} B=2: {eb.activation_bytes / 2**20:.0f} MiB recycled vs {ea.activation_bytes / 2**20:.0f} MiB")
 
 

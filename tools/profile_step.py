@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--cfg", default="yolov3")
     ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--dense", action="store_true", help="also run Darknet.forward (float input packing + dense decode)")
     a = ap.parse_args()
     import bench
     import yolov3_b200
@@ -41,6 +42,11 @@ def main():
         eng.detect(bench.PROB_THRESH, bench.IOU_THRESH)
     torch.cuda.synchronize()
     print("kept", int(eng.det_counts.sum()))
+    if a.dense:
+        x = torch.rand(a.batch, 3, a.size, a.size, device="cuda:0")
+        for _ in range(2):
+            net.forward(x)
+        torch.cuda.synchronize()
 
 
 if __name__ == "__main__":
