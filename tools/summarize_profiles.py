@@ -85,8 +85,15 @@ def launches(src, dst):
 
 
 def raw(src, dst):
-    txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    """src: an .ncu-rep, or the `ncu -i rep --page raw --csv` export of one (reports of a whole step
+    exceed what gpurun brings back, so the GPU box exports the raw page itself)."""
+    if src.endswith(".csv"):
+        txt = open(src).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(txt.splitlines()))
+    while rows and "Kernel Name" not in rows[0]:
+        rows = rows[1:]
     hdr, units, data = rows[0], rows[1], rows[2:]
     cols = [hdr.index(c) for c in RAW_COLS if c in hdr]
     with open(dst, "w") as f:
