@@ -456,3 +456,23 @@ def test_conv_resident_weights_equal_streamed_weights_and_oracle(n, H, W, cin, c
     if res:
         ref = ref + rb.float().cpu().permute(0, 3, 1, 2)
     assert rel_err(outs[0].permute(0, 3, 1, 2), ref) <= CONV_TOL
+
+
+def test_integration_md_ctypes_stub_is_runnable():
+    """The ctypes binding INTEGRATION.md shows a reference maintainer (NMS through the C ABI) is executed
+    verbatim — only the library path is substituted — and must return the oracle's kept set."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", text, re.S) if "y3_nms_workspace_bytes" in b)
+    block = block.replace('ctypes.CDLL("libyolov3_b200.so")', f'ctypes.CDLL("{_lib.LIB_PATH}")')
+    ns = {}
+    exec(block, ns)
+    rng = np.random.default_rng(8)
+    n = 300
+    xy = rng.integers(0, 400, (n, 2))
+    wh = rng.integers(5, 120, (n, 2))
+    tlbr = np.concatenate([xy, xy + wh], 1).astype(np.int64)
+    prob = rng.permutation(np.linspace(0.05, 0.95, n)).astype(np.float32)
+    cls = rng.integers(0, 5, n).astype(np.int64)
+    got = ns["non_max_suppression"](tlbr, prob, cls, 0.3)
+    assert sorted(got) == sorted(PO.nms(tlbr, prob, cls, 0.3))
