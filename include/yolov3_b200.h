@@ -256,7 +256,8 @@ int y3_yolo_decode_cands(const y3_head_desc* d, const float* logits,
  * the fp32 accumulator (+ bias) of each pixel while it is still in tensor memory — the logits never
  * go to HBM.  Requires 3 anchors x 80 classes (255 channels stored as 256; every shipped cfg);
  * otherwise use y3_conv2d (out_f32) + y3_yolo_decode_cands.  The softmax denominator is summed in
- * ascending class order, so a probability may differ from y3_yolo_decode_cands' in the last ulp.
+ * ascending class order with ex2.approx-based exponentials (terms near the maximum carry <= 4 ulp), so
+ * a probability may differ from y3_yolo_decode_cands' by up to ~3e-7 relative.
  */
 int y3_conv2d_yolo_head(const y3_conv_desc* d, const void* x, const void* w,
                         const float* bias, const y3_head_desc* head,
