@@ -44,14 +44,22 @@ __device__ __forceinline__ bool iou_gt(const Box4& a, const Box4& b, double thr)
   return __ddiv_rn(di, du) > thr;
 }
 
-// workspace layout (int32 words): seg_off [N][C+1] | cursor [N][C]
-// class-agnostic mode uses C = 1.
+// workspace layout: bucketed records [N][cap] | seg_off int32 [N][C+1] | four work lists int32 [4][N*C] |
+// four list counters.  class-agnostic mode uses C = 1.
+//
+// Work lists: the bucket kernel files every non-empty (image, class) segment under its size class
+// (<= 128, <= 256, <= 512 boxes, larger) and the suppression kernels run PERSISTENT grids over "their" list.
+// (Launching one CTA per (image, class, size class) instead — 3 x 5120 CTAs for 64 images x 80 classes,
+// most of which exit at once — cost 0.1 ms per launch in block scheduling alone.)
+static constexpr int NUM_LISTS = 4;
+__device__ __forceinline__ int size_class(int n) { return n <= 128 ? 0 : n <= 256 ? 1 : n <= 512 ? 2 : 3; }
 
 __global__ void __launch_bounds__(1024)
 nms_bucket_kernel(const y3_cand* __restrict__ cands, const int* __restrict__ counts, int cap,
                   int num_classes, int per_class, y3_cand* __restrict__ bucketed,
                   int* __restrict__ seg_off, int* __restrict__ class_first_box,
-                  int* __restrict__ class_start) {
+                  int* __restrict__ class_start, int* __restrict__ class_kept, int* __restrict__ lists,
+                  int* __restrict__ list_counts, int list_stride) {
   pdl_enter();
   __shared__ int hist[MAX_CLASSES];
   __shared__ int first[MAX_CLASSES];
@@ -83,6 +91,16 @@ nms_bucket_kernel(const y3_cand* __restrict__ cands, const int* __restrict__ cou
   }
   if (class_first_box)
     for (int c = threadIdx.x; c < C; c += blockDim.x) class_first_box[(long long)img * C + c] = first[c];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // file the segment under its size class
+    const int len = hist[c];
+    if (len == 0) {
+      if (class_kept) class_kept[(long long)img * C + c] = 0;
+    } else {
+      const int k = size_class(len);
+      lists[k * list_stride + atomicAdd(list_counts + k, 1)] = img * C + c;
+    }
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) hist[c] = 0;  // reuse as cursors
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(1024)
 nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
                    int cap, int C, double thr, const y3_thresholds* __restrict__ dyn,
                    y3_cand* __restrict__ sorted, uint8_t* __restrict__ keep, int* __restrict__ class_kept,
-                   int min_n) {
+                   const int* __restrict__ list, const int* __restrict__ list_count) {
   pdl_enter();
   if (dyn) thr = dyn->iou_thresh;  // device-resident thresholds: one graph, any setting
   __shared__ int4 sbox[BITMASK_MAX];
@@ -125,15 +143,14 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
   __shared__ int skey_b[BITMASK_MAX];
   __shared__ uint32_t smask[BITMASK_MAX * BITMASK_WORDS];
   __shared__ uint32_t kept_mask_s;
-  const int img = blockIdx.y;
-  const int seg = blockIdx.x;
+  const int items = *list_count;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+  __syncthreads();  // the previous segment's shared state is dead
+  const int id = list[item];
+  const int img = id / C;
+  const int seg = id - img * C;
   const int off = seg_off[(long long)img * (C + 1) + seg];
   const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
-  if (n <= 0) {
-    if (class_kept && threadIdx.x == 0) class_kept[(long long)img * C + seg] = 0;
-    return;
-  }
-  if (n < min_n) return;  // done by nms_bitmask_kernel
   const y3_cand* src = bucketed + (long long)img * cap + off;
   y3_cand* out = sorted + (long long)img * cap + off;
   uint8_t* keep_out = keep + (long long)img * cap + off;
@@ -219,7 +236,7 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
       for (int o = 16; o > 0; o >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, o);
       if (class_kept && lane == 0) class_kept[(long long)img * C + seg] = nkept;
     }
-    return;
+    continue;
   }
 
   // ---- large segment: rank sort straight from global memory ---------------------------------
@@ -303,6 +320,7 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) class_kept[(long long)img * C + seg] = (int)kept_mask_s;
   }
+  }  // work list
 }
 
 // Segments of up to FAST_SEG_MAX boxes — every per-class segment of a real detector output — in three
@@ -318,7 +336,7 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
 // inside the band, or involving a box with huge or degenerate coordinates (area stored as NaN, which
 // fails both band comparisons), evaluate the reference's int64 / float64 expression (iou_gt) — the
 // kept set stays bit-exact.  Larger segments are left to nms_segment_kernel.
-static constexpr int FAST_SEG_MAX = 512;
+static constexpr int FAST_SEG_MAX = 512;  // = the upper bound of size_class() 2
 
 __device__ __forceinline__ float fast_area(int x1, int y1, int x2, int y2) {
   const bool small = x1 > -4194304 && x1 <= x2 && x2 < 4194304 && y1 > -4194304 && y1 <= y2 && y2 < 4194304;
@@ -329,7 +347,8 @@ template <int MAXN>
 __global__ void __launch_bounds__(MAXN)
 nms_bitmask_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off, int cap, int C,
                    double thr, const y3_thresholds* __restrict__ dyn, y3_cand* __restrict__ sorted,
-                   uint8_t* __restrict__ keep, int* __restrict__ class_kept, int min_n) {
+                   uint8_t* __restrict__ keep, int* __restrict__ class_kept, const int* __restrict__ list,
+                   const int* __restrict__ list_count) {
   pdl_enter();
   if (dyn) thr = dyn->iou_thresh;
   constexpr int WORDS = MAXN / 32;
@@ -338,15 +357,14 @@ nms_bitmask_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
   __shared__ uint2 skey[MAXN];
   __shared__ uint32_t smask[WORDS][MAXN + 1];  // [w][i]; +1: the scan reads one column across w
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x;
-  const int img = blockIdx.y;
-  const int seg = blockIdx.x;
+  const int items = *list_count;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+  __syncthreads();  // the previous segment's shared state is dead
+  const int id = list[item];
+  const int img = id / C;
+  const int seg = id - img * C;
   const int off = seg_off[(long long)img * (C + 1) + seg];
-  const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
-  if (n <= 0) {
-    if (class_kept && t == 0) class_kept[(long long)img * C + seg] = 0;
-    return;
-  }
-  if (n <= min_n || n > MAXN) return;  // another size class (or nms_segment_kernel) owns this segment
+  const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;  // 1 .. MAXN by construction of the list
   const y3_cand* src = bucketed + (long long)img * cap + off;
   y3_cand* out = sorted + (long long)img * cap + off;
   uint8_t* keep_out = keep + (long long)img * cap + off;
@@ -461,6 +479,7 @@ nms_bitmask_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
     for (int o = 16; o > 0; o >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, o);
     if (class_kept && lane == 0) class_kept[(long long)img * C + seg] = nkept;
   }
+  }  // work list
 }
 
 // a17: the three arrays `inference` returns per image (yolov3/inference.py:360-366), written
@@ -615,7 +634,8 @@ size_t y3_nms_workspace_bytes(int32_t n, int32_t cap, int32_t num_classes) {
   if (n <= 0 || cap <= 0 || num_classes <= 0) return 0;
   const size_t bucketed = (size_t)n * cap * sizeof(y3_cand);
   const size_t seg = (size_t)n * ((size_t)num_classes + 1) * sizeof(int32_t);
-  return bucketed + ((seg + 255) / 256) * 256 + 256;
+  const size_t lists = (size_t)NUM_LISTS * n * num_classes * sizeof(int32_t);
+  return bucketed + ((seg + 255) / 256) * 256 + ((lists + 255) / 256) * 256 + 512;
 }
 
 int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, int32_t num_classes,
@@ -636,26 +656,35 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
   cudaStream_t s = (cudaStream_t)stream;
   const int C = per_class ? num_classes : 1;
   y3_cand* bucketed = reinterpret_cast<y3_cand*>(workspace);
-  int* seg_off = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)n * cap * sizeof(y3_cand));
+  uint8_t* const ws8 = reinterpret_cast<uint8_t*>(workspace);
+  int* seg_off = reinterpret_cast<int*>(ws8 + (size_t)n * cap * sizeof(y3_cand));
+  const size_t seg_bytes = (((size_t)n * ((size_t)C + 1) * sizeof(int32_t)) + 255) / 256 * 256;
+  int* lists = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(seg_off) + seg_bytes);
+  const int list_stride = n * C;
+  int* list_counts = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(lists) +
+                                            (((size_t)NUM_LISTS * list_stride * sizeof(int32_t)) + 255) / 256 * 256);
+  Y3_CUDA_OK(cudaMemsetAsync(list_counts, 0, NUM_LISTS * sizeof(int), s));
 
   Y3_CUDA_OK(launch_kernel(nms_bucket_kernel, dim3(n), dim3(1024), 0, s, cands, counts, cap, num_classes, per_class, bucketed, seg_off,
-                           class_first_box, class_start));
+                           class_first_box, class_start, class_kept, lists, list_counts, list_stride));
   Y3_LAUNCH_OK("nms_bucket_kernel");
+  const long long segs = (long long)n * C;
+  auto grid_for = [&](int per_sm) { const long long g = (long long)num_sms() * per_sm; return (int)(segs < g ? segs : g); };
 
   // segments of <= FAST_SEG_MAX boxes: three size classes of the fp32 bit-matrix kernel; the rest (if any):
-  // nms_segment_kernel.  Each launch covers every segment and returns at once for foreign sizes.
-  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<128>, dim3(C, n), dim3(128), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           dev_thresholds, sorted, keep, class_kept, 0));
+  // nms_segment_kernel.  Each launch is a persistent grid over the work list of its size class.
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<128>, dim3(grid_for(16)), dim3(128), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           dev_thresholds, sorted, keep, class_kept, lists, list_counts));
   Y3_LAUNCH_OK("nms_bitmask_kernel<128>");
-  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<256>, dim3(C, n), dim3(256), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           dev_thresholds, sorted, keep, class_kept, 128));
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<256>, dim3(grid_for(8)), dim3(256), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           dev_thresholds, sorted, keep, class_kept, lists + list_stride, list_counts + 1));
   Y3_LAUNCH_OK("nms_bitmask_kernel<256>");
-  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<512>, dim3(C, n), dim3(512), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           dev_thresholds, sorted, keep, class_kept, 256));
+  Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<512>, dim3(grid_for(4)), dim3(512), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           dev_thresholds, sorted, keep, class_kept, lists + 2 * list_stride, list_counts + 2));
   Y3_LAUNCH_OK("nms_bitmask_kernel<512>");
   const int threads = per_class ? 256 : 1024;  // one huge segment per image: more threads per CTA
-  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(dim3(C, n)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh, dev_thresholds,
-                           sorted, keep, class_kept, FAST_SEG_MAX + 1));
+  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(grid_for(2)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh,
+                           dev_thresholds, sorted, keep, class_kept, lists + 3 * list_stride, list_counts + 3));
   Y3_LAUNCH_OK("nms_segment_kernel");
   return Y3_OK;
 }
