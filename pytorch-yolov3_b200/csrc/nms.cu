@@ -4,12 +4,12 @@
 // Three kernels, all integer / fp64-compare work on a few hundred KB per image:
 //   1. nms_bucket_kernel   one CTA per image: class histogram in shared memory, exclusive
 //                          scan, scatter of the candidates into per-class segments.
-//   2. nms_segment_kernel  one CTA per (image, class) segment: rank-sort the segment by
-//                          (prob desc, box asc); segments of <= 512 boxes build the full
-//                          "i suppresses j" bit matrix in shared memory (ballot per 32 boxes) and
-//                          one warp scans it in score order; larger segments go 32 pivots at a
-//                          time (32x32 mask by shuffles, resolved with ballots, then every thread
-//                          tests its later boxes against the chunk's KEPT pivots only).
+//   2. nms_bitmask_kernel  (image, class) segments of <= 128 / 256 / 512 boxes: rank sort in shared
+//                          memory, the full "i suppresses j" bit matrix (fp32 test with an exact
+//                          fallback inside a guard band), one warp scans it in score order.
+//      nms_segment_kernel  larger segments: bitonic sort in shared memory, then 32 pivots at a time
+//                          (32x32 mask by shuffles, resolved with ballots, every thread tests its
+//                          later boxes against the chunk's KEPT pivots only), boxes in shared memory.
 //   3. nms_compact_kernel  ordered compaction of the kept records (block scan).
 // IoU follows the reference exactly: "+1" pixel areas in int64, iou = inter/union as an IEEE
 // float64 divide, suppressed iff iou > thresh.
@@ -120,16 +120,25 @@ __device__ __forceinline__ bool before(float pa, int ba, float pb, int bb) {
   return pa > pb || (pa == pb && ba < bb);
 }
 
-// Segments of up to BITMASK_MAX boxes (every realistic per-class segment) take the bitmask path:
-// keys and boxes are staged in shared memory, rank-sorted there, all threads fill the
-// n x ceil(n/32) "i suppresses j" bit matrix (one IoU test per lane, rows reduced with
-// __ballot_sync), then ONE warp resolves the greedy order 32 boxes at a time: the 32x32 diagonal
-// block is walked with a register-only dependency chain, and the rows of the chunk's KEPT boxes
-// are OR-ed into the later words of the removed set (lane w owns bits [32w, 32w+32)).
-// Larger segments (class-agnostic NMS over thousands of boxes) use the chunked pivot scheme
-// below, with the output `keep` bytes doubling as the alive flags.
-static constexpr int BITMASK_MAX = 512;
-static constexpr int BITMASK_WORDS = BITMASK_MAX / 32;
+// ---- large segments (> 512 boxes: class-agnostic NMS, or a class that dominates an image) --------------
+// One CTA of 1024 threads per segment, shared memory instead of global memory for everything hot:
+//   1. sort: the 64-bit keys (prob descending, box ascending) are bitonic-sorted in shared memory
+//      (up to SEG_SORT_MAX boxes, 128 KB); every source record then finds its rank by binary search of its
+//      own key (keys are unique: box indices are) and is copied to its sorted position.  Larger segments
+//      fall back to the O(n^2) rank count straight from global memory.
+//   2. greedy suppression, 32 pivots at a time: warp 0 resolves the 32 x 32 block among the pivots with
+//      shuffles / ballots, then every thread tests its later, still alive boxes against the chunk's KEPT
+//      pivots only.  Boxes (and alive flags) live in shared memory when the segment fits (SEG_SMEM_BOXES).
+static constexpr int SEG_SORT_MAX = 16384;    // keys: 8 B each
+static constexpr int SEG_SMEM_BOXES = 7168;   // boxes 16 B + alive 1 B each: 119 KB
+static constexpr int SEG_SMEM_BYTES = SEG_SORT_MAX * 8;
+
+// monotone map: larger prob -> smaller key; equal prob -> smaller box first
+__device__ __forceinline__ unsigned long long seg_key(uint32_t prob_bits, uint32_t box) {
+  if (prob_bits == 0x80000000u) prob_bits = 0u;  // -0 == +0, as in before()
+  const uint32_t asc = prob_bits ^ ((prob_bits >> 31) ? 0xffffffffu : 0x80000000u);  // float order as unsigned
+  return ((unsigned long long)(~asc) << 32) | box;
+}
 
 __global__ void __launch_bounds__(1024)
 nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__ seg_off,
@@ -138,192 +147,151 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
                    const int* __restrict__ list, const int* __restrict__ list_count) {
   pdl_enter();
   if (dyn) thr = dyn->iou_thresh;  // device-resident thresholds: one graph, any setting
-  __shared__ int4 sbox[BITMASK_MAX];
-  __shared__ float skey_p[BITMASK_MAX];
-  __shared__ int skey_b[BITMASK_MAX];
-  __shared__ uint32_t smask[BITMASK_MAX * BITMASK_WORDS];
+  extern __shared__ __align__(16) uint8_t seg_smem[];
   __shared__ uint32_t kept_mask_s;
-  const int items = *list_count;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-  __syncthreads();  // the previous segment's shared state is dead
-  const int id = list[item];
-  const int img = id / C;
-  const int seg = id - img * C;
-  const int off = seg_off[(long long)img * (C + 1) + seg];
-  const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
-  const y3_cand* src = bucketed + (long long)img * cap + off;
-  y3_cand* out = sorted + (long long)img * cap + off;
-  uint8_t* keep_out = keep + (long long)img * cap + off;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int items = *list_count;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    __syncthreads();  // the previous segment's shared state is dead
+    const int id = list[item];
+    const int img = id / C;
+    const int seg = id - img * C;
+    const int off = seg_off[(long long)img * (C + 1) + seg];
+    const int n = seg_off[(long long)img * (C + 1) + seg + 1] - off;
+    const y3_cand* src = bucketed + (long long)img * cap + off;
+    y3_cand* out = sorted + (long long)img * cap + off;
+    uint8_t* keep_out = keep + (long long)img * cap + off;
 
-  if (n <= BITMASK_MAX) {
-    // ---- rank sort by (prob desc, box asc), keys in shared memory ---------------------------
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
-      skey_p[i] = __uint_as_float(hi.x);
-      skey_b[i] = (int)hi.z;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
-      const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
-      const float p = __uint_as_float(hi.x);
-      const int b = (int)hi.z;
-      int rank = 0;
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) rank += before(skey_p[j], skey_b[j], p, b) ? 1 : 0;
-      reinterpret_cast<uint4*>(out + rank)[0] = lo;
-      reinterpret_cast<uint4*>(out + rank)[1] = hi;
-      sbox[rank] = make_int4((int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w);
-    }
-    __syncthreads();
-    // ---- bit matrix: word (i, w) holds, for j = 32w + lane, [j > i and iou(i, j) > thr] ----
-    const int words = (n + 31) >> 5;
-    for (int item = warp; item < n * words; item += nwarps) {
-      const int i = item / words;
-      const int w = item - i * words;
-      if (32 * w + 31 <= i) {  // every j of this word precedes i: nothing to suppress
-        if (lane == 0) smask[item] = 0u;
-        continue;
-      }
-      const int j = 32 * w + lane;
-      bool sup = false;
-      if (j < n && j > i) {
-        const int4 bi = sbox[i], bj = sbox[j];
-        sup = iou_gt(Box4{bi.x, bi.y, bi.z, bi.w}, Box4{bj.x, bj.y, bj.z, bj.w}, thr);
-      }
-      const uint32_t word = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0) smask[item] = word;
-    }
-    __syncthreads();
-    // ---- greedy scan, 32 boxes per step ---------------------------------------------------------
-    if (warp == 0) {
-      uint32_t removed = 0;  // lane w: bits [32w, 32w+32) of the removed set
-      for (int c = 0; c < words; ++c) {
-        const int i0 = 32 * c;
-        const int cnt = min(32, n - i0);
-        // diagonal block: lane t holds which boxes of this chunk box i0+t suppresses
-        const uint32_t diag = (lane < cnt) ? smask[(i0 + lane) * words + c] : 0u;
-        uint32_t rem = __shfl_sync(0xffffffffu, removed, c);
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const uint32_t dt = __shfl_sync(0xffffffffu, diag, t);  // independent of the chain on `rem`
-          if (!((rem >> t) & 1u)) rem |= dt;
+    // ---- 1. sort by (prob desc, box asc) -------------------------------------------------------------
+    if (n <= SEG_SORT_MAX) {
+      unsigned long long* skeys = reinterpret_cast<unsigned long long*>(seg_smem);
+      int np = 1024;
+      while (np < n) np <<= 1;
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        unsigned long long k = ~0ull;  // padding sorts last
+        if (i < n) {
+          const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+          k = seg_key(hi.x, hi.z);
         }
-        if (lane == c) removed = rem;
-        uint32_t kept = ~rem & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));  // warp-uniform
-        if (lane > c && lane < words) {
-          while (kept) {
-            const int t = __ffs(kept) - 1;
-            kept &= kept - 1;
-            removed |= smask[(i0 + t) * words + lane];
+        skeys[i] = k;
+      }
+      __syncthreads();
+      for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const unsigned long long a = skeys[i], b = skeys[ixj];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) { skeys[i] = b; skeys[ixj] = a; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {  // rank of record i = position of its key
+        const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+        const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+        const unsigned long long key = seg_key(hi.x, hi.z);
+        int lo_i = 0, hi_i = n - 1;
+        while (lo_i < hi_i) {
+          const int mid = (lo_i + hi_i) >> 1;
+          if (skeys[mid] < key) lo_i = mid + 1; else hi_i = mid;
+        }
+        reinterpret_cast<uint4*>(out + lo_i)[0] = lo;
+        reinterpret_cast<uint4*>(out + lo_i)[1] = hi;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
+        const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
+        const float p = __uint_as_float(hi.x);
+        const int b = (int)hi.z;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const uint4 hj = reinterpret_cast<const uint4*>(src + j)[1];
+          rank += before(__uint_as_float(hj.x), (int)hj.z, p, b) ? 1 : 0;
+        }
+        reinterpret_cast<uint4*>(out + rank)[0] = lo;
+        reinterpret_cast<uint4*>(out + rank)[1] = hi;
+      }
+    }
+    __syncthreads();  // global writes to `out` by this CTA are visible to it from here on; the keys are dead
+
+    // ---- 2. greedy suppression, 32 pivots at a time --------------------------------------------------
+    const bool in_smem = n <= SEG_SMEM_BOXES;
+    int4* sboxes = reinterpret_cast<int4*>(seg_smem);
+    volatile uint8_t* alive = in_smem ? reinterpret_cast<volatile uint8_t*>(seg_smem + (size_t)SEG_SMEM_BOXES * 16)
+                                      : reinterpret_cast<volatile uint8_t*>(keep_out);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (in_smem) sboxes[i] = reinterpret_cast<const int4*>(out + i)[0];
+      alive[i] = 1;
+    }
+    __syncthreads();
+    auto box_at = [&](int j) -> Box4 {
+      const int4 v = in_smem ? sboxes[j] : reinterpret_cast<const int4*>(out + j)[0];
+      return Box4{v.x, v.y, v.z, v.w};
+    };
+    for (int c0 = 0; c0 < n; c0 += 32) {
+      if (warp == 0) {
+        const int j = c0 + lane;
+        const bool valid = j < n;
+        Box4 mine = {0, 0, 0, 0};
+        if (valid) mine = box_at(j);
+        const bool was_alive = valid && alive[valid ? j : 0];
+        // bit i of sup: pivot i (earlier in order) would suppress me
+        uint32_t sup = 0;
+        for (int i = 0; i < 32; ++i) {
+          Box4 pi;
+          pi.x1 = __shfl_sync(0xffffffffu, mine.x1, i);
+          pi.y1 = __shfl_sync(0xffffffffu, mine.y1, i);
+          pi.x2 = __shfl_sync(0xffffffffu, mine.x2, i);
+          pi.y2 = __shfl_sync(0xffffffffu, mine.y2, i);
+          if (i < lane && valid && iou_gt(pi, mine, thr)) sup |= 1u << i;
+        }
+        uint32_t kept = 0;
+        for (int i = 0; i < 32; ++i) {
+          const bool k = (lane == i) && was_alive && ((sup & kept) == 0);
+          kept |= __ballot_sync(0xffffffffu, k);
+        }
+        if (valid) alive[j] = (kept >> lane) & 1u;
+        if (lane == 0) kept_mask_s = kept;
+      }
+      __syncthreads();
+      const uint32_t kept = kept_mask_s;
+      if (kept != 0) {
+        for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
+          if (!alive[j]) continue;
+          const Box4 mine = box_at(j);
+          uint32_t m = kept;
+          while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            if (iou_gt(box_at(c0 + i), mine, thr)) { alive[j] = 0; break; }
           }
         }
       }
-      // box i is kept iff no earlier kept box set its bit
-      int nkept = 0;
-      for (int b = 0; b < 32; ++b) {
-        const int i = 32 * lane + b;
-        if (i < n) {
-          const int k = ((removed >> b) & 1u) ? 0 : 1;
-          keep_out[i] = (uint8_t)k;
-          nkept += k;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, o);
-      if (class_kept && lane == 0) class_kept[(long long)img * C + seg] = nkept;
+      __syncthreads();
     }
-    continue;
-  }
-
-  // ---- large segment: rank sort straight from global memory ---------------------------------
-  volatile uint8_t* alive = keep_out;  // written and re-read by different threads of this CTA
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const uint4 lo = reinterpret_cast<const uint4*>(src + i)[0];
-    const uint4 hi = reinterpret_cast<const uint4*>(src + i)[1];
-    const float p = __uint_as_float(hi.x);
-    const int b = (int)hi.z;
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      const uint4 hj = reinterpret_cast<const uint4*>(src + j)[1];
-      rank += before(__uint_as_float(hj.x), (int)hj.z, p, b) ? 1 : 0;
-    }
-    reinterpret_cast<uint4*>(out + rank)[0] = lo;
-    reinterpret_cast<uint4*>(out + rank)[1] = hi;
-    alive[i] = 1;
-  }
-  __syncthreads();  // global writes to `out` / `alive` by this CTA are visible to it from here on
-
-  // ---- large segment: greedy suppression, 32 pivots at a time ----------------------------
-  for (int c0 = 0; c0 < n; c0 += 32) {
-    if (warp == 0) {
-      const int j = c0 + lane;
-      const bool valid = j < n;
-      Box4 mine = {0, 0, 0, 0};
-      if (valid) {
-        const int4 v = reinterpret_cast<const int4*>(out + j)[0];
-        mine = {v.x, v.y, v.z, v.w};
-      }
-      const bool was_alive = valid && alive[valid ? j : 0];
-      // bit i of sup: pivot i (earlier in order) would suppress me
-      uint32_t sup = 0;
-      for (int i = 0; i < 32; ++i) {
-        Box4 pi;
-        pi.x1 = __shfl_sync(0xffffffffu, mine.x1, i);
-        pi.y1 = __shfl_sync(0xffffffffu, mine.y1, i);
-        pi.x2 = __shfl_sync(0xffffffffu, mine.x2, i);
-        pi.y2 = __shfl_sync(0xffffffffu, mine.y2, i);
-        if (i < lane && valid && iou_gt(pi, mine, thr)) sup |= 1u << i;
-      }
-      uint32_t kept = 0;
-      for (int i = 0; i < 32; ++i) {
-        const bool k = (lane == i) && was_alive && ((sup & kept) == 0);
-        kept |= __ballot_sync(0xffffffffu, k);
-      }
-      if (valid) {
-        const uint8_t k = (kept >> lane) & 1u;
-        alive[j] = k;
-        keep_out[j] = k;
-      }
-      if (lane == 0) kept_mask_s = kept;
-    }
-    __syncthreads();
-    const uint32_t kept = kept_mask_s;
-    if (kept != 0) {
-      for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
-        if (!alive[j]) continue;
-        const int4 v = reinterpret_cast<const int4*>(out + j)[0];
-        const Box4 mine = {v.x, v.y, v.z, v.w};
-        uint32_t m = kept;
-        while (m) {
-          const int i = __ffs(m) - 1;
-          m &= m - 1;
-          const int4 pv = reinterpret_cast<const int4*>(out + c0 + i)[0];
-          const Box4 pivot = {pv.x, pv.y, pv.z, pv.w};
-          if (iou_gt(pivot, mine, thr)) { alive[j] = 0; break; }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (class_kept) {
+    // ---- 3. flags out, kept count -----------------------------------------------------------------------
     if (threadIdx.x == 0) kept_mask_s = 0u;
     __syncthreads();
     int local = 0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) local += alive[j];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const uint8_t k = alive[j];
+      if (in_smem) keep_out[j] = k;
+      local += k;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if (lane == 0 && local) atomicAdd(&kept_mask_s, (uint32_t)local);
     __syncthreads();
-    if (threadIdx.x == 0) class_kept[(long long)img * C + seg] = (int)kept_mask_s;
-  }
+    if (class_kept && threadIdx.x == 0) class_kept[(long long)img * C + seg] = (int)kept_mask_s;
   }  // work list
 }
 
-// Segments of up to FAST_SEG_MAX boxes — every per-class segment of a real detector output — in three
+// Segments of up to 512 boxes — every per-class segment of a real detector output — in three
 // size classes (<= 128, <= 256, <= 512 boxes), one CTA of MAXN threads per (image, class):
 //   1. rank sort by (prob desc, box asc) through shared memory; the sorted boxes are kept there as
 //      fp32 (x1, y1, x2+1, y2+1) + area;
@@ -336,7 +304,6 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
 // inside the band, or involving a box with huge or degenerate coordinates (area stored as NaN, which
 // fails both band comparisons), evaluate the reference's int64 / float64 expression (iou_gt) — the
 // kept set stays bit-exact.  Larger segments are left to nms_segment_kernel.
-static constexpr int FAST_SEG_MAX = 512;  // = the upper bound of size_class() 2
 
 __device__ __forceinline__ float fast_area(int x1, int y1, int x2, int y2) {
   const bool small = x1 > -4194304 && x1 <= x2 && x2 < 4194304 && y1 > -4194304 && y1 <= y2 && y2 < 4194304;
@@ -671,7 +638,7 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
   const long long segs = (long long)n * C;
   auto grid_for = [&](int per_sm) { const long long g = (long long)num_sms() * per_sm; return (int)(segs < g ? segs : g); };
 
-  // segments of <= FAST_SEG_MAX boxes: three size classes of the fp32 bit-matrix kernel; the rest (if any):
+  // segments of <= 512 boxes: three size classes of the fp32 bit-matrix kernel; the rest (if any):
   // nms_segment_kernel.  Each launch is a persistent grid over the work list of its size class.
   Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<128>, dim3(grid_for(16)), dim3(128), 0, s, bucketed, seg_off, cap, C, iou_thresh,
                            dev_thresholds, sorted, keep, class_kept, lists, list_counts));
@@ -682,9 +649,14 @@ int y3_nms(const y3_cand* cands, const int32_t* counts, int32_t n, int32_t cap, 
   Y3_CUDA_OK(launch_kernel(nms_bitmask_kernel<512>, dim3(grid_for(4)), dim3(512), 0, s, bucketed, seg_off, cap, C, iou_thresh,
                            dev_thresholds, sorted, keep, class_kept, lists + 2 * list_stride, list_counts + 2));
   Y3_LAUNCH_OK("nms_bitmask_kernel<512>");
-  const int threads = per_class ? 256 : 1024;  // one huge segment per image: more threads per CTA
-  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(grid_for(2)), dim3(threads), 0, s, bucketed, seg_off, cap, C, iou_thresh,
-                           dev_thresholds, sorted, keep, class_kept, lists + 3 * list_stride, list_counts + 3));
+  static bool seg_attr = false;
+  if (!seg_attr) {
+    Y3_CUDA_OK(cudaFuncSetAttribute(nms_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_SMEM_BYTES));
+    seg_attr = true;
+  }
+  Y3_CUDA_OK(launch_kernel(nms_segment_kernel, dim3(grid_for(1)), dim3(1024), (size_t)SEG_SMEM_BYTES, s, bucketed, seg_off, cap,
+                           C, iou_thresh, dev_thresholds, sorted, keep, class_kept, lists + 3 * list_stride,
+                           list_counts + 3));
   Y3_LAUNCH_OK("nms_segment_kernel");
   return Y3_OK;
 }

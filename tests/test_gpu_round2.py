@@ -476,3 +476,28 @@ def test_integration_md_ctypes_stub_is_runnable():
     cls = rng.integers(0, 5, n).astype(np.int64)
     got = ns["non_max_suppression"](tlbr, prob, cls, 0.3)
     assert sorted(got) == sorted(PO.nms(tlbr, prob, cls, 0.3))
+
+
+@pytest.mark.parametrize("n,iou", [(513, 0.3), (1024, 0.3), (1025, 0.5), (5000, 0.3), (7168, 0.45), (7169, 0.3),
+                                   (10647, 0.3), (16384, 0.6), (16500, 0.3)])
+def test_nms_large_segments_bit_exact(n, iou):
+    """Class-agnostic NMS = one large segment: the shared-memory bitonic sort (<= 16384 boxes), boxes staged in
+    shared memory (<= 7168) or read from global memory, and the O(n^2) rank-sort fallback beyond — kept
+    indices identical, in order, to the C restatement of the reference (yolov3/inference.py:161-217)."""
+    from test_gpu_parity import stress_candidates
+    tlbr, prob, cls = stress_candidates(np.random.default_rng(n), n, 80, size=608)
+    assert yolov3_b200.non_max_suppression(tlbr, prob, None, iou) == nms_c.nms(tlbr, prob, None, iou)
+
+
+def test_nms_dominant_class_takes_the_large_segment_path():
+    """Per-class NMS where one class owns most of an image's candidates (what random-weight yolov3-spp@608
+    produces): segments of 3 sizes classes + a > 512-box one in the same image, batch of 3."""
+    from test_gpu_parity import stress_candidates
+    rng = np.random.default_rng(5)
+    n = 4000
+    tlbr, prob, cls = stress_candidates(rng, n, 80, size=608)
+    cls = np.where(rng.random(n) < 0.6, 7, cls)            # class 7: ~2400 boxes
+    cls = np.where((cls != 7) & (rng.random(n) < 0.3), 3, cls)   # class 3: a few hundred
+    got = yolov3_b200.non_max_suppression(tlbr, prob, cls, 0.3)
+    assert got == nms_c.nms(tlbr, prob, cls, 0.3)
+    assert (cls == 7).sum() > 512
