@@ -130,8 +130,10 @@ __device__ __forceinline__ bool before(float pa, int ba, float pb, int bb) {
 //      shuffles / ballots, then every thread tests its later, still alive boxes against the chunk's KEPT
 //      pivots only.  Boxes (and alive flags) live in shared memory when the segment fits (SEG_SMEM_BOXES).
 static constexpr int SEG_SORT_MAX = 16384;    // keys: 8 B each
-static constexpr int SEG_SMEM_BOXES = 7168;   // boxes 16 B + alive 1 B each: 119 KB
+static constexpr int SEG_SMEM_BOXES = 6144;   // fp32 box 16 B + area 4 B + alive 1 B each: 126 KB
 static constexpr int SEG_SMEM_BYTES = SEG_SORT_MAX * 8;
+
+__device__ __forceinline__ float fast_area(int x1, int y1, int x2, int y2);
 
 // monotone map: larger prob -> smaller key; equal prob -> smaller box first
 __device__ __forceinline__ unsigned long long seg_key(uint32_t prob_bits, uint32_t box) {
@@ -220,36 +222,58 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
     __syncthreads();  // global writes to `out` by this CTA are visible to it from here on; the keys are dead
 
     // ---- 2. greedy suppression, 32 pivots at a time --------------------------------------------------
+    // in_smem: boxes as fp32 (x1, y1, x2+1, y2+1) + fp32 area + alive flags in shared memory; the IoU test is
+    // the bitmask kernel's: fp32 with a 2^-18 guard band around the threshold, the reference's exact int64 /
+    // fp64 expression (iou_gt on the int records in `out`) only inside the band or for huge / degenerate boxes.
     const bool in_smem = n <= SEG_SMEM_BOXES;
-    int4* sboxes = reinterpret_cast<int4*>(seg_smem);
-    volatile uint8_t* alive = in_smem ? reinterpret_cast<volatile uint8_t*>(seg_smem + (size_t)SEG_SMEM_BOXES * 16)
+    float4* sbf = reinterpret_cast<float4*>(seg_smem);
+    float* sar = reinterpret_cast<float*>(seg_smem + (size_t)SEG_SMEM_BOXES * 16);
+    volatile uint8_t* alive = in_smem ? reinterpret_cast<volatile uint8_t*>(seg_smem + (size_t)SEG_SMEM_BOXES * 20)
                                       : reinterpret_cast<volatile uint8_t*>(keep_out);
+    const double cd = thr / (1.0 + thr);
+    const bool band_ok = thr > 1e-6 && thr < 1e6;  // the guard band assumes a positive finite threshold
+    const float c_hi = band_ok ? (float)cd * (1.0f + 3.814697265625e-06f) : __int_as_float(0x7fc00000);  // 1 + 2^-18
+    const float c_lo = band_ok ? (float)cd * (1.0f - 3.814697265625e-06f) : __int_as_float(0x7fc00000);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      if (in_smem) sboxes[i] = reinterpret_cast<const int4*>(out + i)[0];
+      if (in_smem) {
+        const int4 v = reinterpret_cast<const int4*>(out + i)[0];
+        sbf[i] = make_float4((float)v.x, (float)v.y, (float)v.z + 1.0f, (float)v.w + 1.0f);
+        sar[i] = fast_area(v.x, v.y, v.z, v.w);
+      }
       alive[i] = 1;
     }
     __syncthreads();
-    auto box_at = [&](int j) -> Box4 {
-      const int4 v = in_smem ? sboxes[j] : reinterpret_cast<const int4*>(out + j)[0];
-      return Box4{v.x, v.y, v.z, v.w};
+    // does box i (earlier in score order) suppress box j?
+    auto suppresses = [&](int i, int j) -> bool {
+      if (in_smem) {
+        const float4 pv = sbf[i], mb = sbf[j];
+        const float s2 = sar[i] + sar[j];
+        const float iw = fminf(pv.z, mb.z) - fmaxf(pv.x, mb.x);
+        const float ih = fminf(pv.w, mb.w) - fmaxf(pv.y, mb.y);
+        const float fi = fmaxf(iw, 0.f) * fmaxf(ih, 0.f);
+        if (fi > c_hi * s2) return true;
+        if (fi <= c_lo * s2) return false;
+      }
+      const int4 a = reinterpret_cast<const int4*>(out + i)[0];
+      const int4 b = reinterpret_cast<const int4*>(out + j)[0];
+      return iou_gt(Box4{a.x, a.y, a.z, a.w}, Box4{b.x, b.y, b.z, b.w}, thr);
     };
+    __shared__ uint32_t s_sup[32];  // s_sup[w]: which boxes of the chunk pivot w would suppress
     for (int c0 = 0; c0 < n; c0 += 32) {
+      {  // 32 x 32 block among the chunk's boxes: warp w = pivot c0 + w, lane l = box c0 + l (blockDim = 1024)
+        const int i = c0 + warp, j = c0 + lane;
+        const bool s = warp < lane && j < n && suppresses(i, j);
+        const uint32_t word = __ballot_sync(0xffffffffu, s);
+        if (lane == 0) s_sup[warp] = word;
+      }
+      __syncthreads();
       if (warp == 0) {
         const int j = c0 + lane;
         const bool valid = j < n;
-        Box4 mine = {0, 0, 0, 0};
-        if (valid) mine = box_at(j);
         const bool was_alive = valid && alive[valid ? j : 0];
-        // bit i of sup: pivot i (earlier in order) would suppress me
-        uint32_t sup = 0;
-        for (int i = 0; i < 32; ++i) {
-          Box4 pi;
-          pi.x1 = __shfl_sync(0xffffffffu, mine.x1, i);
-          pi.y1 = __shfl_sync(0xffffffffu, mine.y1, i);
-          pi.x2 = __shfl_sync(0xffffffffu, mine.x2, i);
-          pi.y2 = __shfl_sync(0xffffffffu, mine.y2, i);
-          if (i < lane && valid && iou_gt(pi, mine, thr)) sup |= 1u << i;
-        }
+        uint32_t sup = 0;  // bit w: pivot w (earlier in order) would suppress me
+#pragma unroll
+        for (int w = 0; w < 32; ++w) sup |= ((s_sup[w] >> lane) & 1u) << w;
         uint32_t kept = 0;
         for (int i = 0; i < 32; ++i) {
           const bool k = (lane == i) && was_alive && ((sup & kept) == 0);
@@ -263,12 +287,11 @@ nms_segment_kernel(const y3_cand* __restrict__ bucketed, const int* __restrict__
       if (kept != 0) {
         for (int j = c0 + 32 + threadIdx.x; j < n; j += blockDim.x) {
           if (!alive[j]) continue;
-          const Box4 mine = box_at(j);
           uint32_t m = kept;
           while (m) {
             const int i = __ffs(m) - 1;
             m &= m - 1;
-            if (iou_gt(box_at(c0 + i), mine, thr)) { alive[j] = 0; break; }
+            if (suppresses(c0 + i, j)) { alive[j] = 0; break; }
           }
         }
       }

@@ -478,11 +478,11 @@ def test_integration_md_ctypes_stub_is_runnable():
     assert sorted(got) == sorted(PO.nms(tlbr, prob, cls, 0.3))
 
 
-@pytest.mark.parametrize("n,iou", [(513, 0.3), (1024, 0.3), (1025, 0.5), (5000, 0.3), (7168, 0.45), (7169, 0.3),
+@pytest.mark.parametrize("n,iou", [(513, 0.3), (1024, 0.3), (1025, 0.5), (5000, 0.3), (6144, 0.45), (6145, 0.3),
                                    (10647, 0.3), (16384, 0.6), (16500, 0.3)])
 def test_nms_large_segments_bit_exact(n, iou):
     """Class-agnostic NMS = one large segment: the shared-memory bitonic sort (<= 16384 boxes), boxes staged in
-    shared memory (<= 7168) or read from global memory, and the O(n^2) rank-sort fallback beyond — kept
+    shared memory (<= 6144) or read from global memory, and the O(n^2) rank-sort fallback beyond — kept
     indices identical, in order, to the C restatement of the reference (yolov3/inference.py:161-217)."""
     from test_gpu_parity import stress_candidates
     tlbr, prob, cls = stress_candidates(np.random.default_rng(n), n, 80, size=608)
