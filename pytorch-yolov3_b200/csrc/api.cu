@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <immintrin.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -50,6 +52,38 @@ int num_sms() {
   return cached_sms;
 }
 
+// memcpy with non-temporal stores: the staging buffer is written once and read by the DMA engine, never by
+// a core, so the destination lines need neither a read-for-ownership nor a place in the caches (one third
+// less DRAM traffic per staged byte, which is what eight ranks staging 33 MB per batch compete for).
+__attribute__((target("avx2"))) static void stream_copy_avx2(char* dst, const char* src, size_t len) {
+  const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+  if (head >= len) { memcpy(dst, src, len); return; }
+  memcpy(dst, src, head);
+  dst += head; src += head; len -= head;
+  size_t i = 0;
+  for (; i + 128 <= len; i += 128) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+  }
+  _mm_sfence();
+  if (i < len) memcpy(dst + i, src + i, len - i);
+}
+
+static bool use_stream_copy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_STAGE_NT");
+    v = (e ? e[0] == '1' : true) && __builtin_cpu_supports("avx2") ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // Host staging pool of y3_stage_images: parked worker threads (created once, never joined — the pool
 // is leaked on purpose so nothing is torn down under a waiting thread at process exit) copy 256 KB
 // chunks of the stacked batch handed out by an atomic counter; the caller copies along with them.
@@ -62,6 +96,7 @@ class StagePool {
     if (helpers > chunks - 1) helpers = (int)(chunks - 1);
     std::unique_lock<std::mutex> call(call_mu_);  // one batch at a time
     dst_ = dst; srcs_ = srcs; bytes_each_ = bytes_each; total_ = total; chunks_ = chunks;
+    nt_ = use_stream_copy();
     next_.store(0, std::memory_order_relaxed);
     if (helpers > 0) {
       std::lock_guard<std::mutex> lk(mu_);
@@ -94,7 +129,8 @@ class StagePool {
       while (left > 0) {  // a chunk may straddle images
         const long long img = off / bytes_each_, in = off - img * bytes_each_;
         const long long len = bytes_each_ - in < left ? bytes_each_ - in : left;
-        memcpy(dst_ + off, static_cast<const char*>(srcs_[img]) + in, (size_t)len);
+        if (nt_) stream_copy_avx2(dst_ + off, static_cast<const char*>(srcs_[img]) + in, (size_t)len);
+        else memcpy(dst_ + off, static_cast<const char*>(srcs_[img]) + in, (size_t)len);
         off += len;
         left -= len;
       }
@@ -125,6 +161,7 @@ class StagePool {
   char* dst_ = nullptr;
   const void* const* srcs_ = nullptr;
   long long bytes_each_ = 0, total_ = 0, chunks_ = 0;
+  bool nt_ = false;
   std::atomic<long long> next_{0};
 };
 

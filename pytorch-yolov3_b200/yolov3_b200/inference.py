@@ -27,7 +27,8 @@ _TRACE = os.environ.get("Y3_TRACE", "0") == "1"
 _JITTER_MS = float(os.environ.get("Y3_STRESS_JITTER_MS", "0"))
 # host threads that stage a batch into pinned memory: the box's cores shared between the ranks of a node
 # (torchrun exports LOCAL_WORLD_SIZE), at most 16 — beyond that the copy is memory-bound
-_STAGE_THREADS = max(2, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+_STAGE_THREADS = int(os.environ.get("Y3_STAGE_THREADS", "0")) or max(
+    2, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 
 def cxywh_to_tlbr(bbox_xywh):
@@ -325,8 +326,11 @@ class _Slot:
         self.img = _pinned((B, H, W, 3), torch.uint8)
         self.hw = _pinned((B, 2), torch.int32)
         self.meta = _pinned((self.eng.meta.numel(),), torch.int32)
-        self.ev_meta = torch.cuda.Event()
-        self.ev_out = torch.cuda.Event()
+        # blocking events: the host thread sleeps in synchronize() instead of spinning on a core the staging
+        # threads (and, under torchrun, the other ranks) can use.  Y3_SPIN_SYNC=1 restores the spin wait.
+        blocking = os.environ.get("Y3_SPIN_SYNC", "0") != "1"
+        self.ev_meta = torch.cuda.Event(blocking=blocking)
+        self.ev_out = torch.cuda.Event(blocking=blocking)
 
 
 def _reorder_to_set_order(res, class_kept_row, first_box_row):
@@ -345,7 +349,7 @@ def _reorder_to_set_order(res, class_kept_row, first_box_row):
 
 
 def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thresh=0.3, resize=True, depth=3,
-                      gather=None):
+                      gather=None, stats=None):
     """``inference`` over a stream of batches, pipelined: a generator that yields, in order, exactly
     what ``inference(net, batch, ...)`` returns for every batch of ``batches`` (an iterable of image
     lists; a bare ndarray counts as a one-image batch).
@@ -359,12 +363,19 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
 
     ``gather``: optional ``distributed.DetectionGather`` — every batch's kept detections are also
     gathered, device to device, on its destination rank (all ranks must iterate in lock step).
+    ``stats``: optional dict; receives the host seconds spent staging images (``stage``), queueing work
+    (``submit``), waiting for a batch's kernels (``wait_gpu``) and for its download (``wait_copy``), and
+    building the result lists (``build``), summed over the batches.
     """
     dev = _lib.require_device(device)
     depth = max(2, int(depth))
     pending = deque()
     thr = (float(prob_thresh), float(nms_iou_thresh))
     counters = {}
+
+    def tick(name, seconds):
+        if stats is not None:
+            stats[name] = stats.get(name, 0.0) + seconds
 
     def submit(images):
         net.check_fresh()
@@ -379,8 +390,11 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
             slot = slots[idx % depth]
             while any(it["slot"] is slot for it in pending):  # only when geometries alternate oddly
                 yield_ready.append(finish(pending.popleft()))
+            t0 = time.perf_counter()
             _stack_into(slot.img.numpy(), images)
             slot.hw.numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
+            t1 = time.perf_counter()
+            tick("stage", t1 - t0)
             eng = slot.eng
             with torch.cuda.stream(slot.stream):
                 eng.in_u8.copy_(slot.img, non_blocking=True)
@@ -390,13 +404,17 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
                 if gather is not None:
                     gather.post_counts(eng)
                 slot.ev_meta.record()
+            tick("submit", time.perf_counter() - t1)
         return {"slot": slot, "B": B, "stage": 0}
 
     def stage_a(it):
         """Batch finished on the GPU: read its counts, queue the download of exactly its detections."""
         slot, B = it["slot"], it["B"]
         eng = slot.eng
+        t0 = time.perf_counter()
         slot.ev_meta.synchronize()
+        t1 = time.perf_counter()
+        tick("wait_gpu", t1 - t0)
         per_image, total, class_kept, first_box = _split_meta(slot.meta.numpy(), B, eng.num_classes)
         it["per_image"] = per_image.copy()
         it["total"] = total
@@ -413,12 +431,16 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
             if gather is not None:
                 gather.gather_payload(eng, total)
             slot.ev_out.record()
+        tick("submit", time.perf_counter() - t1)
         it["stage"] = 1
 
     def finish(it):
         if it["stage"] == 0:
             stage_a(it)
+        t0 = time.perf_counter()
         it["slot"].ev_out.synchronize()
+        t1 = time.perf_counter()
+        tick("wait_copy", t1 - t0)
         if not it["total"]:
             return [_empty_result() for _ in range(it["B"])]
         tlbr, prob, cls = (t.numpy() for t in it["out"])
@@ -428,6 +450,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
             pos += k
         for i, ck, fb in it["odd"]:
             results[i] = _reorder_to_set_order(results[i], ck, fb)
+        tick("build", time.perf_counter() - t1)
         return results
 
     yield_ready = []
