@@ -134,14 +134,15 @@ class DetectionGather:
     trips of its own: per batch ONE small ``all_gather`` of every rank's per-image
     detection counts, issued on the stream right behind the batch's CUDA graph, and — once the host has
     read them together with its own counts (it has to wait for those anyway to size its download) — ONE
-    ``gather`` per output array of exactly ``max over ranks`` detections (rounded up to 4096) onto
-    global rank ``dst``.  Every rank derives the same size from the same gathered counts, so no rank
-    waits for another on the host.  Works with NCCL (device tensors) and gloo (CPU tensors, tests).
+    ``gather`` of exactly ``max over ranks`` kept records (32-byte ``y3_cand``, rounded up to 4096 of
+    them) onto global rank ``dst``.  Every rank derives the same size from the same gathered counts, so
+    no rank waits for another on the host.  Works with NCCL (device tensors) and gloo (CPU tensors, tests).
 
     After batch k's payload has been queued, ``last`` = ``(per_rank, counts)`` on ``dst`` — ``per_rank[r]``
-    = ``(tlbr int64 [K_r,4], prob float32 [K_r], cls int64 [K_r])`` views of the receive buffers (valid
-    once the stream has caught up; overwritten by this slot's next batch), ``counts`` int64 numpy
-    ``[world, B]`` — and ``(None, counts)`` elsewhere.
+    = int32 ``[K_r, 8]`` records of rank r's images back to back (per image: class ascending, probability
+    descending; ``engine.records_to_numpy`` widens them to the reference's arrays), views of the receive
+    buffer (valid once the stream has caught up; overwritten by this slot's next batch), ``counts`` int64
+    numpy ``[world, B]`` — and ``(None, counts)`` elsewhere.
     """
 
     def __init__(self, group=None, dst=0):
@@ -169,26 +170,23 @@ class DetectionGather:
         self._queue.append(eng)
 
     def gather_payload(self, eng, total):
-        """Queue the gather of this batch's detections (call once the copy queued by ``post_counts`` has
-        completed, i.e. after the batch's meta event).  ``total`` = this rank's detections."""
+        """Queue the gather of this batch's kept records ``eng.dets`` (call once the copy queued by
+        ``post_counts`` has completed, i.e. after the batch's meta event).  ``total`` = this rank's count."""
         assert self._queue.popleft() is eng, "DetectionGather: batches must be finished in submission order"
         st = eng._gather_state
         B = eng.det_counts_total.numel() - 1
         allc = st["counts_host"].numpy().reshape(self.world, B + 1).astype(np.int64)
         assert int(allc[self.rank if self.group is None else dist.get_rank(self.group), B]) == int(total)
-        cap = eng.out_prob.shape[0]
+        cap = eng.dets.shape[0]
         n = min(cap, max(4096, (int(allc[:, B].max()) + 4095) // 4096 * 4096))
-        srcs = (eng.out_tlbr, eng.out_prob, eng.out_cls)
         if self.rank == self.dst and "recv" not in st:
-            st["recv"] = [torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in srcs]
-        for j, t in enumerate(srcs):
-            bufs = [st["recv"][j][r, :n] for r in range(self.world)] if self.rank == self.dst else None
-            dist.gather(t[:n], bufs, dst=self.dst, group=self.group)
-            self.bytes_gathered += n * t[0].numel() * t.element_size() * (self.world if self.rank == self.dst else 1)
+            st["recv"] = torch.empty((self.world,) + tuple(eng.dets.shape), dtype=eng.dets.dtype, device=eng.dets.device)
+        bufs = [st["recv"][r, :n] for r in range(self.world)] if self.rank == self.dst else None
+        dist.gather(eng.dets[:n], bufs, dst=self.dst, group=self.group)
+        self.bytes_gathered += n * 32 * (self.world if self.rank == self.dst else 1)
         counts = allc[:, :B]
         if self.rank == self.dst:
-            per_rank = [tuple(st["recv"][j][r, :int(allc[r, B])] for j in range(3)) for r in range(self.world)]
-            self.last = (per_rank, counts)
+            self.last = ([st["recv"][r, :int(allc[r, B])] for r in range(self.world)], counts)
         else:
             self.last = (None, counts)
         return self.last

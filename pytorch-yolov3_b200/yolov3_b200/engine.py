@@ -667,6 +667,11 @@ class Engine:
                 if self.stem is None:
                     pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
                 self._detect(compact=False, fused_stem=True, emit=True)
+        elif kind == "gather_u8":  # emit_u8 + flat y3_cand records for the multi-GPU gather (one collective)
+            def fn():
+                if self.stem is None:
+                    pack_u8(self.in_u8, self.in_view.buf, self.in_view.C)
+                self._detect(compact=True, fused_stem=True, emit=True)
         elif kind == "det_f32":
             def fn():
                 pack_f32(self.in_f32, self.in_view.buf, self.in_view.C)

@@ -13,6 +13,8 @@ receives the arrays; class groups follow the reference's ``set(class_idx)`` visi
 There is no CPU implementation here.
 """
 import os
+import queue
+import threading
 import time
 from collections import deque
 
@@ -313,24 +315,65 @@ def last_device_outputs(net, batch, height, width, device):
 # batched, pipelined loop (the CLI's image-directory / frame loops)
 # ----------------------------------------------------------------------------------------------
 class _Slot:
-    """One in-flight batch of ``inference_batches``: its own execution plan (buffers + CUDA graph),
-    stream and pinned staging memory."""
+    """One in-flight batch of ``inference_batches``: its own execution plan (buffers + CUDA graph) and
+    stream."""
 
     def __init__(self, net, B, H, W, index, dev):
         # plans that run side by side on different streams are captured without programmatic dependent
-        # launch (a parked dependent CTA would hold an SM the neighbouring batch could use)
+        # launch (DESIGN.md §6: PDL + concurrent graphs deadlock)
         self.eng = net.engine(B, H, W, slot=100 + index, concurrent=True)
         if self.eng.device != dev:
             raise RuntimeError(f"net runs on {self.eng.device}, device '{dev}' requested")
         self.stream = torch.cuda.Stream(device=dev)
-        self.img = _pinned((B, H, W, 3), torch.uint8)
-        self.hw = _pinned((B, 2), torch.int32)
         self.meta = _pinned((self.eng.meta.numel(),), torch.int32)
         # blocking events: the host thread sleeps in synchronize() instead of spinning on a core the staging
         # threads (and, under torchrun, the other ranks) can use.  Y3_SPIN_SYNC=1 restores the spin wait.
         blocking = os.environ.get("Y3_SPIN_SYNC", "0") != "1"
         self.ev_meta = torch.cuda.Event(blocking=blocking)
         self.ev_out = torch.cuda.Event(blocking=blocking)
+
+
+class _Stager(threading.Thread):
+    """Background half of ``inference_batches``: pulls batches from the caller's iterable, validates /
+    resizes them and stacks them into pinned buffers (a ring of ``depth + 1`` per geometry, so it runs up
+    to two batches ahead of the GPU).  The copy happens inside the library without the interpreter lock,
+    so it overlaps the main thread's queueing, waiting and result building."""
+
+    def __init__(self, net, batches, resize, ring, stats, dev):
+        super().__init__(daemon=True, name="y3-stager")
+        self.net, self.batches, self.resize, self.ring, self.stats, self.dev = net, batches, resize, ring, stats, dev
+        self.out = queue.Queue(maxsize=ring)
+        self.free = {}      # geometry -> queue of free (img, hw) pinned buffer pairs
+        self.stop = False
+
+    def buffers(self, B, H, W):
+        q = self.free.get((B, H, W))
+        if q is None:
+            q = self.free[(B, H, W)] = queue.Queue()
+            for _ in range(self.ring):
+                q.put((_pinned((B, H, W, 3), torch.uint8), _pinned((B, 2), torch.int32)))
+        return q
+
+    def run(self):
+        try:
+            torch.cuda.set_device(self.dev)  # pinned allocations of this thread belong to the plan's device
+            for images in self.batches:
+                if self.stop:
+                    break
+                images, orig_shapes, B, H, W = _prepare(self.net, images, self.resize)
+                q = self.buffers(B, H, W)
+                bufs = q.get()  # blocks until the GPU has consumed an earlier batch's buffer
+                if self.stop:
+                    break
+                t1 = time.perf_counter()
+                _stack_into(bufs[0].numpy(), images)
+                bufs[1].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
+                if self.stats is not None:
+                    self.stats["stage"] = self.stats.get("stage", 0.0) + time.perf_counter() - t1
+                self.out.put(("batch", (B, H, W), bufs, q))
+            self.out.put(("end", None, None, None))
+        except BaseException as e:  # noqa: BLE001 - re-raised in the consumer thread
+            self.out.put(("error", e, None, None))
 
 
 def _reorder_to_set_order(res, class_kept_row, first_box_row):
@@ -354,58 +397,56 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
     what ``inference(net, batch, ...)`` returns for every batch of ``batches`` (an iterable of image
     lists; a bare ndarray counts as a one-image batch).
 
-    While batch k runs on the GPU (one CUDA-graph replay on its own stream and plan), the host stages
-    and uploads batch k+1 and downloads / hands out batch k-1, so neither PCIe nor host work sits
-    between two batches' kernels.  Up to ``depth`` batches are in flight (>= 2; each holds one plan:
+    While batch k runs on the GPU (one CUDA-graph replay on its own stream and plan), a background thread
+    stages batch k+1 / k+2 into pinned memory (the iterable is consumed from that thread) and the calling
+    thread uploads k+1 and downloads / hands out batch k-1, so neither PCIe nor host work sits between two
+    batches' kernels.  Up to ``depth`` batches are in flight (>= 2; each holds one plan:
     activations + graph).  The final int64 / float32 arrays are written on the device inside the same
     graph (class groups ascending) and land in pinned host arrays; images whose ``set(class_idx)``
     order is not ascending (fewer than 19 distinct classes) are re-ordered on the host.
 
     ``gather``: optional ``distributed.DetectionGather`` — every batch's kept detections are also
     gathered, device to device, on its destination rank (all ranks must iterate in lock step).
-    ``stats``: optional dict; receives the host seconds spent staging images (``stage``), queueing work
-    (``submit``), waiting for a batch's kernels (``wait_gpu``) and for its download (``wait_copy``), and
-    building the result lists (``build``), summed over the batches.
+    ``stats``: optional dict; receives the host seconds spent staging images (``stage``, background thread),
+    waiting for the stager (``wait_stage``), queueing work (``submit``), waiting for a batch's kernels
+    (``wait_gpu``) and for its download (``wait_copy``), and building the result lists (``build``), summed
+    over the batches.
     """
     dev = _lib.require_device(device)
     depth = max(2, int(depth))
     pending = deque()
     thr = (float(prob_thresh), float(nms_iou_thresh))
     counters = {}
+    program = "gather_u8" if gather is not None else "emit_u8"
 
     def tick(name, seconds):
         if stats is not None:
             stats[name] = stats.get(name, 0.0) + seconds
 
-    def submit(images):
-        net.check_fresh()
-        images, orig_shapes, B, H, W = _prepare(net, images, resize)
+    def submit(geom_key, bufs, free_q):
+        t1 = time.perf_counter()
+        B, H, W = geom_key
         geom = net.geometry(B, H, W)
         slots = geom.setdefault("pipe", [])
-        idx = counters.get((B, H, W), 0)
-        counters[(B, H, W)] = idx + 1
+        idx = counters.get(geom_key, 0)
+        counters[geom_key] = idx + 1
         with torch.cuda.device(dev):
             if len(slots) <= idx % depth:
                 slots.append(_Slot(net, B, H, W, len(slots), dev))
             slot = slots[idx % depth]
             while any(it["slot"] is slot for it in pending):  # only when geometries alternate oddly
                 yield_ready.append(finish(pending.popleft()))
-            t0 = time.perf_counter()
-            _stack_into(slot.img.numpy(), images)
-            slot.hw.numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
-            t1 = time.perf_counter()
-            tick("stage", t1 - t0)
             eng = slot.eng
             with torch.cuda.stream(slot.stream):
-                eng.in_u8.copy_(slot.img, non_blocking=True)
-                eng.orig_hw.copy_(slot.hw, non_blocking=True)
-                eng.launch(("emit_u8",) + thr)
+                eng.in_u8.copy_(bufs[0], non_blocking=True)
+                eng.orig_hw.copy_(bufs[1], non_blocking=True)
+                eng.launch((program,) + thr)
                 slot.meta.copy_(eng.meta, non_blocking=True)
                 if gather is not None:
                     gather.post_counts(eng)
                 slot.ev_meta.record()
-            tick("submit", time.perf_counter() - t1)
-        return {"slot": slot, "B": B, "stage": 0}
+        tick("submit", time.perf_counter() - t1)
+        return {"slot": slot, "B": B, "stage": 0, "bufs": bufs, "free_q": free_q}
 
     def stage_a(it):
         """Batch finished on the GPU: read its counts, queue the download of exactly its detections."""
@@ -415,6 +456,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
         slot.ev_meta.synchronize()
         t1 = time.perf_counter()
         tick("wait_gpu", t1 - t0)
+        it["free_q"].put(it["bufs"])  # its upload is long done: the stager may refill the pinned buffers
         per_image, total, class_kept, first_box = _split_meta(slot.meta.numpy(), B, eng.num_classes)
         it["per_image"] = per_image.copy()
         it["total"] = total
@@ -453,17 +495,40 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
         tick("build", time.perf_counter() - t1)
         return results
 
+    net.check_fresh()
+    stager = _Stager(net, batches, resize, depth + 1, stats, dev)
+    stager.start()
     yield_ready = []
-    for images in batches:
-        pending.append(submit(images))
-        while yield_ready:
-            yield yield_ready.pop(0)
-        if len(pending) >= 2 and pending[-2]["stage"] == 0:
-            stage_a(pending[-2])
-        while len(pending) >= depth:
+    try:
+        while True:
+            t0 = time.perf_counter()
+            kind, a_, bufs, free_q = stager.out.get()
+            tick("wait_stage", time.perf_counter() - t0)
+            if kind == "end":
+                break
+            if kind == "error":
+                raise a_
+            pending.append(submit(a_, bufs, free_q))
+            while yield_ready:
+                yield yield_ready.pop(0)
+            if len(pending) >= 2 and pending[-2]["stage"] == 0:
+                stage_a(pending[-2])
+            while len(pending) >= depth:
+                yield finish(pending.popleft())
+        while pending:
             yield finish(pending.popleft())
-    while pending:
-        yield finish(pending.popleft())
+    finally:
+        stager.stop = True
+        for q in list(stager.free.values()):  # wake a stager that waits for a buffer (generator closed early)
+            q.put((None, None))
+        try:
+            while True:  # ... or for room in the hand-over queue
+                stager.out.get_nowait()
+        except queue.Empty:
+            pass
+        while pending:  # never leave device work behind that still reads the pinned buffers
+            it = pending.popleft()
+            it["slot"].stream.synchronize()
 
 
 def non_max_suppression(bbox_tlbr, class_prob, class_idx=None, iou_thresh=0.3):

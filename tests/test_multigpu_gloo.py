@@ -99,14 +99,11 @@ class _FakePlan:
         per = [len(r[1]) for r in results]
         self.det_counts_total = torch.tensor(per + [sum(per)], dtype=torch.int32)
         self.B = B
-        self.out_tlbr = torch.zeros(cap, 4, dtype=torch.int64)
-        self.out_prob = torch.zeros(cap, dtype=torch.float32)
-        self.out_cls = torch.zeros(cap, dtype=torch.int64)
+        self.dets = torch.zeros(cap, 8, dtype=torch.int32)
         k = sum(per)
         if k:
-            self.out_tlbr[:k] = torch.from_numpy(np.concatenate([r[0] for r in results]))
-            self.out_prob[:k] = torch.from_numpy(np.concatenate([r[1] for r in results]))
-            self.out_cls[:k] = torch.from_numpy(np.concatenate([r[2] for r in results]))
+            from yolov3_b200.distributed import pack_results
+            self.dets[:k] = torch.from_numpy(pack_results(results)[0])
 
 
 def _gather_worker(rank, world, port, q):
@@ -133,9 +130,9 @@ def _gather_worker(rank, world, port, q):
         for batch, (per_rank, counts) in zip(everything, outs):
             ok = ok and counts.reshape(-1).tolist() == [len(r[1]) for r in batch]
             if rank == 0:
-                for j in range(3):
-                    whole = np.concatenate([pr[j].numpy() for pr in per_rank])
-                    ok = ok and np.array_equal(whole, np.concatenate([r[j] for r in batch]))
+                rec = np.concatenate([pr.numpy() for pr in per_rank])
+                got = D.unpack_results(rec, counts.reshape(-1))
+                ok = ok and all(np.array_equal(x, y) for g, b in zip(got, batch) for x, y in zip(g, b))
             else:
                 ok = ok and per_rank is None
         # gather_outputs on a sub-group whose destination is NOT global rank 0

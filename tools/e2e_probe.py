@@ -14,6 +14,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "pytorch-yolov3_b200"))
 
 
+KEYS = ("stage", "wait_stage", "submit", "wait_gpu", "wait_copy", "build")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", type=int, default=60)
@@ -54,7 +57,7 @@ def main():
     if world > 1:
         dist.barrier()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt] + [stats.get(k, 0.0) for k in ("stage", "submit", "wait_gpu", "wait_copy", "build")],
+    t = torch.tensor([dt] + [stats.get(k, 0.0) for k in KEYS],
                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -63,7 +66,7 @@ def main():
         per = [round(x / a.batches * 1e3, 3) for x in v[1:]]
         print(json.dumps({"tag": a.tag, "world": world, "images_per_s": round(world * 64 * a.batches / v[0]),
                           "ms_per_batch": round(v[0] / a.batches * 1e3, 3),
-                          "host_ms_per_batch_max_over_ranks": dict(zip(("stage", "submit", "wait_gpu", "wait_copy", "build"), per)),
+                          "host_ms_per_batch_max_over_ranks": dict(zip(KEYS, per)),
                           "env": {k: os.environ.get(k) for k in ("Y3_SPIN_SYNC", "Y3_STAGE_NT", "Y3_STAGE_THREADS")}}), flush=True)
     del net, gather
     torch.cuda.synchronize()
