@@ -134,15 +134,19 @@ class DetectionGather:
     trips of its own: per batch ONE small ``all_gather`` of every rank's per-image
     detection counts, issued on the stream right behind the batch's CUDA graph, and — once the host has
     read them together with its own counts (it has to wait for those anyway to size its download) — ONE
-    ``gather`` of exactly ``max over ranks`` kept records (32-byte ``y3_cand``, rounded up to 4096 of
-    them) onto global rank ``dst``.  Every rank derives the same size from the same gathered counts, so
-    no rank waits for another on the host.  Works with NCCL (device tensors) and gloo (CPU tensors, tests).
+    ``all_gather`` of exactly ``max over ranks`` kept records (32-byte ``y3_cand``, rounded up to 4096 of
+    them).  Every rank derives the same size from the same gathered counts, so no rank waits for another
+    on the host.  (An all-gather rather than a gather onto one rank: over NVSwitch it is a single ring /
+    NVLS kernel and one host call, where the grouped send/recv of a rooted gather cost ~2 ms of host time
+    per batch at 8 ranks — measured, tools/e2e_probe.py — and made the root's GPU the straggler.)  Works
+    with NCCL (device tensors) and gloo (CPU tensors, tests).
 
-    After batch k's payload has been queued, ``last`` = ``(per_rank, counts)`` on ``dst`` — ``per_rank[r]``
-    = int32 ``[K_r, 8]`` records of rank r's images back to back (per image: class ascending, probability
+    After batch k's payload has been queued, ``last`` = ``(per_rank, counts)`` — on every rank when
+    ``dst`` is None, else on global rank ``dst`` only (``(None, counts)`` elsewhere): ``per_rank[r]`` =
+    int32 ``[K_r, 8]`` records of rank r's images back to back (per image: class ascending, probability
     descending; ``engine.records_to_numpy`` widens them to the reference's arrays), views of the receive
     buffer (valid once the stream has caught up; overwritten by this slot's next batch), ``counts`` int64
-    numpy ``[world, B]`` — and ``(None, counts)`` elsewhere.
+    numpy ``[world, B]``.
     """
 
     def __init__(self, group=None, dst=0):
@@ -179,14 +183,14 @@ class DetectionGather:
         assert int(allc[self.rank if self.group is None else dist.get_rank(self.group), B]) == int(total)
         cap = eng.dets.shape[0]
         n = min(cap, max(4096, (int(allc[:, B].max()) + 4095) // 4096 * 4096))
-        if self.rank == self.dst and "recv" not in st:
-            st["recv"] = torch.empty((self.world,) + tuple(eng.dets.shape), dtype=eng.dets.dtype, device=eng.dets.device)
-        bufs = [st["recv"][r, :n] for r in range(self.world)] if self.rank == self.dst else None
-        dist.gather(eng.dets[:n], bufs, dst=self.dst, group=self.group)
-        self.bytes_gathered += n * 32 * (self.world if self.rank == self.dst else 1)
+        if "recv" not in st:
+            st["recv"] = torch.empty((self.world * cap, 8), dtype=eng.dets.dtype, device=eng.dets.device)
+        recv = st["recv"][:self.world * n]
+        dist.all_gather_into_tensor(recv.view(-1), eng.dets[:n].reshape(-1), group=self.group)
+        self.bytes_gathered += n * 32 * self.world
         counts = allc[:, :B]
-        if self.rank == self.dst:
-            self.last = ([st["recv"][r, :int(allc[r, B])] for r in range(self.world)], counts)
+        if self.dst is None or self.rank == self.dst:
+            self.last = ([recv[r * n:r * n + int(allc[r, B])] for r in range(self.world)], counts)
         else:
             self.last = (None, counts)
         return self.last

@@ -2,10 +2,4 @@
 N=${N:-8}
 run() { env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) tools/e2e_probe.py --tag "$*" $EXTRA 2>/dev/null | tail -1; }
 nproc
-run Y3_SPIN_SYNC=1 Y3_STAGE_NT=0
-run Y3_SPIN_SYNC=0 Y3_STAGE_NT=0
-run Y3_SPIN_SYNC=0 Y3_STAGE_NT=1
-run Y3_SPIN_SYNC=1 Y3_STAGE_NT=1
-run Y3_SPIN_SYNC=0 Y3_STAGE_NT=1 Y3_STAGE_THREADS=2
-run Y3_SPIN_SYNC=0 Y3_STAGE_NT=1 Y3_STAGE_THREADS=8
-EXTRA=--no-gather run Y3_SPIN_SYNC=0 Y3_STAGE_NT=1
+run Y3_STAGE_NT=1
