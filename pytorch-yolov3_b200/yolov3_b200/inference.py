@@ -101,6 +101,41 @@ def _pinned(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
+# page-locked image buffers handed out by pinned_images(): base address -> (tensor [n,H,W,3], bytes per image)
+_PINNED_IMAGES = {}
+
+
+def pinned_images(n, height, width):
+    """A uint8 ``[n, height, width, 3]`` host array in page-locked memory, for callers that own their frame
+    buffers (a capture ring, a decoder's output pool).  Batches whose images are consecutive views of such
+    an array are uploaded by DMA straight from it; any other array is first stacked into a pinned staging
+    buffer by the library's host threads (one extra pass over host memory).  Do not overwrite the images
+    of a batch before ``inference`` returned / ``inference_batches`` yielded its results."""
+    t = torch.empty((n, height, width, 3), dtype=torch.uint8, pin_memory=True)
+    a = t.numpy()
+    _PINNED_IMAGES[a.ctypes.data] = (t, height * width * 3)
+    return a
+
+
+def _pinned_view(images, H, W):
+    """The pinned tensor slice ``[B, H, W, 3]`` the batch's images are consecutive views of, or None."""
+    if not _PINNED_IMAGES:
+        return None
+    per = H * W * 3
+    p0 = images[0].ctypes.data
+    for base, (t, nbytes_img) in _PINNED_IMAGES.items():
+        if nbytes_img != per or not (base <= p0 < base + t.numel()) or (p0 - base) % per:
+            continue
+        first = (p0 - base) // per
+        if first + len(images) > t.shape[0]:
+            return None
+        for i, im in enumerate(images):
+            if not im.flags.c_contiguous or im.ctypes.data != p0 + i * per:
+                return None
+        return t[first:first + len(images)]
+    return None
+
+
 def _stack_into(dst, images):
     """``np.stack(images)`` straight into the pinned staging buffer: plain memcpy's on a few host
     threads of the library (no interpreter lock held); non-contiguous inputs are compacted first."""
@@ -366,7 +401,11 @@ class _Stager(threading.Thread):
                 if self.stop:
                     break
                 t1 = time.perf_counter()
-                _stack_into(bufs[0].numpy(), images)
+                direct = _pinned_view(images, H, W)
+                if direct is not None:
+                    bufs = (bufs[0], bufs[1], direct)  # upload from the caller's page-locked images
+                else:
+                    _stack_into(bufs[0].numpy(), images)
                 bufs[1].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
                 if self.stats is not None:
                     self.stats["stage"] = self.stats.get("stage", 0.0) + time.perf_counter() - t1
@@ -438,7 +477,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
                 yield_ready.append(finish(pending.popleft()))
             eng = slot.eng
             with torch.cuda.stream(slot.stream):
-                eng.in_u8.copy_(bufs[0], non_blocking=True)
+                eng.in_u8.copy_(bufs[2] if len(bufs) == 3 else bufs[0], non_blocking=True)
                 eng.orig_hw.copy_(bufs[1], non_blocking=True)
                 eng.launch((program,) + thr)
                 slot.meta.copy_(eng.meta, non_blocking=True)
@@ -456,7 +495,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
         slot.ev_meta.synchronize()
         t1 = time.perf_counter()
         tick("wait_gpu", t1 - t0)
-        it["free_q"].put(it["bufs"])  # its upload is long done: the stager may refill the pinned buffers
+        it["free_q"].put(it["bufs"][:2])  # its upload is long done: the stager may refill the pinned buffers
         per_image, total, class_kept, first_box = _split_meta(slot.meta.numpy(), B, eng.num_classes)
         it["per_image"] = per_image.copy()
         it["total"] = total

@@ -501,3 +501,20 @@ def test_nms_dominant_class_takes_the_large_segment_path():
     got = yolov3_b200.non_max_suppression(tlbr, prob, cls, 0.3)
     assert got == nms_c.nms(tlbr, prob, cls, 0.3)
     assert (cls == 7).sum() > 512
+
+
+def test_pinned_frame_buffers_skip_the_staging_copy_and_change_nothing(yolov3_full):
+    """Images that are consecutive views of a yolov3_b200.pinned_images() array are uploaded straight from
+    it; scattered views and ordinary arrays go through the staging copy — same detections either way."""
+    from yolov3_b200.inference import _pinned_view
+    net, *_ = yolov3_full
+    rng = np.random.default_rng(21)
+    frames = yolov3_b200.pinned_images(12, 416, 416)
+    frames[...] = rng.integers(0, 256, frames.shape, dtype=np.uint8)
+    batches = [list(frames[0:4]), list(frames[4:8]), [frames[9], frames[8], frames[11], frames[10]], list(frames[8:12].copy())]
+    assert _pinned_view(batches[0], 416, 416) is not None and _pinned_view(batches[1], 416, 416) is not None
+    assert _pinned_view(batches[2], 416, 416) is None and _pinned_view(batches[3], 416, 416) is None
+    got = list(yolov3_b200.inference_batches(net, batches, device="cuda:0", prob_thresh=0.05, resize=False))
+    for b, g in zip(batches, got):
+        want = yolov3_b200.inference(net, [np.array(im) for im in b], device="cuda:0", prob_thresh=0.05, resize=False)
+        assert same_results(g, want)

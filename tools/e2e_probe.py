@@ -9,6 +9,8 @@ import os
 import sys
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "pytorch-yolov3_b200"))
@@ -39,6 +41,13 @@ def main():
         dist.barrier()
     net = yolov3_b200.Darknet(bench.CFG, device=str(dev)).load_weights(bench.weights_file()).eval()
     lists = [list(bench.synth_images(64, 1234 + 17 * rank + i)) for i in range(4)]
+    if os.environ.get("Y3_PROBE_PINNED", "1") == "1":
+        pl = []
+        for b in lists:
+            frames = yolov3_b200.pinned_images(64, 416, 416)
+            frames[...] = np.stack(b)
+            pl.append(list(frames))
+        lists = pl
     gather = ydist.DetectionGather() if (world > 1 and not a.no_gather) else None
 
     def loop(n, stats=None):
@@ -67,7 +76,7 @@ def main():
         print(json.dumps({"tag": a.tag, "world": world, "images_per_s": round(world * 64 * a.batches / v[0]),
                           "ms_per_batch": round(v[0] / a.batches * 1e3, 3),
                           "host_ms_per_batch_max_over_ranks": dict(zip(KEYS, per)),
-                          "env": {k: os.environ.get(k) for k in ("Y3_SPIN_SYNC", "Y3_STAGE_NT", "Y3_STAGE_THREADS")}}), flush=True)
+                          "env": {k: os.environ.get(k) for k in ("Y3_SPIN_SYNC", "Y3_STAGE_NT", "Y3_STAGE_THREADS", "Y3_PROBE_PINNED")}}), flush=True)
     del net, gather
     torch.cuda.synchronize()
     if world > 1:
