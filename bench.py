@@ -22,9 +22,10 @@ is one pass of the hot path over one batch: uint8 BGR -> bf16 NHWC packing, the 
   sustained : the same loop continued for >= 200 steps (~1 s), where the 1 kW power cap is engaged —
           `value` at the driver's --steps 20 is a burst number; both are reported with their clocks.
   e2e   : the same metric through the public API with HOST images, `yolov3_b200.inference_batches`
-          (the batched loop behind the CLI): pinned H2D of every batch and D2H of its kept detections
-          inside the timed region, batches pipelined.  `e2e.sync_call` = one blocking
-          `yolov3_b200.inference()` call per batch.
+          (the batched loop behind the CLI): H2D of every batch from page-locked frame buffers
+          (`yolov3_b200.pinned_images`) and D2H of its kept detections inside the timed region, batches
+          pipelined.  `e2e.pageable_inputs` = the same call on ordinary numpy arrays (one extra host pass
+          into pinned staging memory); `e2e.sync_call` = one blocking `yolov3_b200.inference()` per batch.
   roofline : tensor-core bound; achieved = algorithmic conv FLOPs per step / summed CUDA-event time of
           the conv launches of one in-order pass over the network (events between launches, so every
           kernel sees the L2 state its real predecessor leaves); `frac_of_step` divides by the whole
@@ -40,7 +41,7 @@ is one pass of the hot path over one batch: uint8 BGR -> bf16 NHWC packing, the 
           pure Python/torch, nothing to compile) timed on all host cores, same metric and config.
 
 Multi-GPU (torchrun, one rank per GPU): images are independent, so ranks run disjoint batches
-(weak scaling); NCCL only gathers detection counts / detections (yolov3_b200.distributed).
+(weak scaling); NCCL only all-gathers detection counts / kept records (yolov3_b200.distributed).
 """
 import argparse
 import faulthandler

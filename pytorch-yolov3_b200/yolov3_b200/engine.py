@@ -35,10 +35,18 @@ def _ceil(x, m):
 
 class View:
     """NHWC tensor view: channel slice ``[c0, c0+C)`` of a buffer with pixel pitch ``ld``."""
-    __slots__ = ("buf", "ptr", "C", "ld", "H", "W", "f32")
+    __slots__ = ("buf", "ptr", "C", "ld", "H", "W", "f32", "raw")
 
-    def __init__(self, buf, ptr, C, ld, H, W, f32=False):
+    def __init__(self, buf, ptr, C, ld, H, W, f32=False, raw=None):
         self.buf, self.ptr, self.C, self.ld, self.H, self.W, self.f32 = buf, ptr, C, ld, H, W, f32
+        self.raw = raw  # the pooled allocation behind `buf` (identity = "same memory")
+
+
+def _check_distinct(what, out, *ins):
+    """Plan-build invariant of the activation pool: an op never writes the allocation it reads."""
+    for v in ins:
+        if v is not None and out.raw is not None and v.raw is out.raw and v.ptr == out.ptr:
+            raise RuntimeError(f"internal error: {what} would write the buffer it reads (activation pool)")
 
 
 class Engine:
@@ -215,10 +223,13 @@ class Engine:
                 n *= d_
             return raw[:n * (4 if dtype == torch.float32 else 2)].view(dtype).view(*dims)
 
+        concat_raw = {}
+
         def concat_of(r):
             if concat_buf[r] is None:
                 C, H, W = shape[r]
-                concat_buf[r] = typed(pool_get(B * H * W * C * 2, last_reader(r)), (B, H, W, C), torch.bfloat16)
+                concat_raw[r] = pool_get(B * H * W * C * 2, last_reader(r))
+                concat_buf[r] = typed(concat_raw[r], (B, H, W, C), torch.bfloat16)
             return concat_buf[r]
 
         def alloc(i, f32=False, c_store=None):
@@ -226,13 +237,14 @@ class Engine:
             if i in placement and not f32:
                 r, off = placement[i]
                 buf = concat_of(r)
-                return View(buf, _p(buf) + off * 2, C, buf.shape[3], H, W)
+                return View(buf, _p(buf) + off * 2, C, buf.shape[3], H, W, raw=concat_raw[r])
             cs = c_store or C
             dtype = torch.float32 if f32 else torch.bfloat16
             # YOLO head logits are read by the decode kernels AFTER the whole backbone: never recycled
             last = FOREVER if f32 else last_reader(i)
-            buf = typed(pool_get(B * H * W * cs * (4 if f32 else 2), last), (B, H, W, cs), dtype)
-            return View(buf, _p(buf), cs, cs, H, W, f32)
+            raw = pool_get(B * H * W * cs * (4 if f32 else 2), last)
+            buf = typed(raw, (B, H, W, cs), dtype)
+            return View(buf, _p(buf), cs, cs, H, W, f32, raw=raw)
 
         # network input.  A first layer that is 3x3/s1/pad1 over <= 3 channels (every shipped cfg)
         # gets its im2col done by the packing kernel: the input buffer holds K = 27 -> 32 taps
@@ -306,6 +318,7 @@ class Engine:
                 tgt = fused_into[i + 1]
                 yv = alloc(tgt)
                 views[tgt] = views[i + 1] = yv
+                _check_distinct(f"chain{i}", yv, xin)
                 w1, b1 = folded(i, 64, 32)
                 w2, b2 = folded(i + 1, 32, 64)
                 fn = (lambda xp=xin.ptr, w1=w1, b1=b1, w2=w2, b2=b2, yp=yv.ptr, h=xin.H, w=xin.W, lx=xin.ld, ly=yv.ld,
@@ -342,6 +355,7 @@ class Engine:
                 if tgt != i:
                     views[i] = yv  # never read (single consumer), kept for introspection
                 res = views[residual_of[i]] if i in residual_of else None
+                _check_distinct(f"conv{i}", yv, xin, res)
                 as_gemm = self.first_im2col and i == 0
                 w, bias = folded(i, xin.C, cout_pad, flatten_taps=as_gemm)
                 kk, pp = (1, 0) if as_gemm else (k, pad)

@@ -163,28 +163,6 @@ def test_inference_batches_equals_inference(yolov3_full, micro):
     assert len(one) == 1 and len(one[0]) == 1
 
 
-def test_set_order_reordering_matches_python_sets():
-    """_reorder_to_set_order on synthetic groups: any class subset, against a real Python set."""
-    from yolov3_b200.inference import _reorder_to_set_order
-    rng = np.random.default_rng(3)
-    for _ in range(200):
-        C = 80
-        n_cls = int(rng.integers(1, 25))
-        classes = rng.choice(C, n_cls, replace=False)
-        cand_cls = rng.permutation(np.repeat(classes, rng.integers(1, 5, n_cls)))  # candidate order
-        first = np.full(C, np.iinfo(np.int32).max, np.int32)
-        kept = np.zeros(C, np.int32)
-        for j, c in enumerate(cand_cls):
-            first[c] = min(first[c], j)
-        for c in classes:
-            kept[c] = rng.integers(1, 4)
-        asc = np.concatenate([np.full(kept[c], c) for c in range(C)])
-        res = [np.stack([asc] * 4, 1).astype(np.int64), asc.astype(np.float32), asc.astype(np.int64)]
-        out = _reorder_to_set_order(res, kept, first)
-        want = np.concatenate([np.full(kept[c], c) for c in set(np.int64(c) for c in cand_cls)])
-        assert np.array_equal(out[2], want)
-
-
 # ------------------------------------------------------------------------------------------
 # spp-608 at its benchmark batch (BASELINE.json configs[2])
 # ------------------------------------------------------------------------------------------
