@@ -493,11 +493,11 @@ def bench_network(wl_name, args, dev, rank, world, sampler, full=True):
         frames[...] = b
         pinned_lists.append(list(frames))
 
-    def e2e_loop(n, lists):
+    def e2e_loop(n, lists, stats=None):
         kept = 0
         gen = yolov3_b200.inference_batches(net, (lists[i % 4] for i in range(n)), device=str(dev),
                                             prob_thresh=PROB_THRESH, nms_iou_thresh=IOU_THRESH, resize=False,
-                                            gather=gather)
+                                            gather=gather, stats=stats)
         for res in gen:
             kept = sum(len(r[1]) for r in res)
         return kept
@@ -505,17 +505,21 @@ def bench_network(wl_name, args, dev, rank, world, sampler, full=True):
     e2e_loop(8, pinned_lists)  # steady state of the pinned-memory cache; NCCL warms up on the first gathers
     barrier()
     t0 = time.perf_counter()
-    kept = e2e_loop(e2e_steps, pinned_lists)
+    host_stats = {}
+    kept = e2e_loop(e2e_steps, pinned_lists, host_stats)
     barrier()
     m["e2e"] = {"dt": time.perf_counter() - t0, "steps": e2e_steps,
+                "host_ms_per_batch": {k: round(v / e2e_steps * 1e3, 3) for k, v in sorted(host_stats.items())},
                 "d2h": kept * 44 + eng.meta.numel() * 4, "h2d": B * S * S * 3 + B * 8,
                 "gathered_bytes_per_step": (gather.bytes_gathered // (2 * e2e_steps + 16)) if gather else 0}
     e2e_loop(8, host_lists)
     barrier()
     t0 = time.perf_counter()
-    e2e_loop(e2e_steps, host_lists)
+    host_stats = {}
+    e2e_loop(e2e_steps, host_lists, host_stats)
     barrier()
-    m["e2e_pageable"] = {"dt": time.perf_counter() - t0, "steps": e2e_steps}
+    m["e2e_pageable"] = {"dt": time.perf_counter() - t0, "steps": e2e_steps,
+                         "host_ms_per_batch": {k: round(v / e2e_steps * 1e3, 3) for k, v in sorted(host_stats.items())}}
     n_sync = 20
     for i in range(4):
         yolov3_b200.inference(net, host_lists[i % 4], device=str(dev), prob_thresh=PROB_THRESH,
@@ -659,9 +663,14 @@ def assemble(wl_name, m, args, world, peaks):
                              "its detections inside the timed region, 3 batches in flight",
                       "pageable_inputs": {"value": world * B * m["e2e_pageable"]["steps"] / m["e2e_pageable"]["dt"],
                                           "unit": "images/s",
+                                          "host_ms_per_batch_rank0": m["e2e_pageable"]["host_ms_per_batch"],
                                           "note": "same call, images in ordinary (pageable) numpy arrays: one extra "
                                                   "host pass stacks them into pinned staging memory"},
                       "nccl_gathered_bytes_per_step": e["gathered_bytes_per_step"],
+                      "host_ms_per_batch": {"rank0": e["host_ms_per_batch"], "host_cores": os.cpu_count(),
+                                            "note": "where rank 0's host time goes per batch: stage = background "
+                                                    "staging thread, wait_gpu = blocked on the batch's kernels (the "
+                                                    "healthy state), submit = queueing copies / graph / collectives"},
                       "sync_call": {"value": world * B * m["e2e_sync"]["steps"] / m["e2e_sync"]["dt"], "unit": "images/s",
                                     "api": "yolov3_b200.inference(net, list_of_uint8_images, resize=False), one blocking "
                                            "call per batch"}}

@@ -12,7 +12,7 @@ helpers are out of scope and keep coming from the reference pack
 INTEGRATION.md for how its CLI binds to this module.
 """
 from .darknet import Darknet, DummyLayer, MaxPool2d, YOLOLayer, blocks2modules, parse_config
-from .inference import cxywh_to_tlbr, inference, inference_batches, non_max_suppression, pinned_images
+from .inference import cxywh_to_tlbr, inference, inference_batches, non_max_suppression, pinned_images, unpin_images
 
-__all__ = ["Darknet", "cxywh_to_tlbr", "non_max_suppression", "inference", "inference_batches", "pinned_images"]
+__all__ = ["Darknet", "cxywh_to_tlbr", "non_max_suppression", "inference", "inference_batches", "pinned_images", "unpin_images"]
 __version__ = "0.1.0"

@@ -117,6 +117,11 @@ def pinned_images(n, height, width):
     return a
 
 
+def unpin_images(array):
+    """Forget a ``pinned_images`` array (its page-locked memory is released once the array itself is)."""
+    _PINNED_IMAGES.pop(array.ctypes.data, None)
+
+
 def _pinned_view(images, H, W):
     """The pinned tensor slice ``[B, H, W, 3]`` the batch's images are consecutive views of, or None."""
     if not _PINNED_IMAGES:
