@@ -89,30 +89,30 @@ def chunks(items, n):
 
 def build_parser():
     p = argparse.ArgumentParser(prog="yolov3")
-    src = p.add_argument_group(title="input source [required]").add_mutually_exclusive_group(required=True)
+    src = p.add_argument_group(title="what to run on (exactly one)").add_mutually_exclusive_group(required=True)
     src.add_argument("-C", "--cam", metavar="cam_id", nargs="?", const=0,
-                     help="Camera or video capture device ID or path. [Default 0]")
+                     help="webcam index or capture-stream path (default: device 0)")
     src.add_argument("-I", "--image", type=pathlib.Path, metavar="<path>",
-                     help="Path to image file or directory of images.")
-    src.add_argument("-V", "--video", type=pathlib.Path, metavar="<path>", help="Path to video file.")
-    m = p.add_argument_group(title="model parameters")
+                     help="one image, or a directory whose images are processed in batches")
+    src.add_argument("-V", "--video", type=pathlib.Path, metavar="<path>", help="video file whose frames are processed in batches")
+    m = p.add_argument_group(title="network and thresholds")
     m.add_argument("-c", "--config", type=pathlib.Path, required=True, metavar="<path>",
-                   help="[Required] Path to Darknet model config file.")
+                   help="Darknet .cfg describing the network (required)")
     m.add_argument("-d", "--device", type=str, default="cuda", metavar="<device>",
-                   help="CUDA device for inference ('cuda', 'cuda:1'). [Default 'cuda'] (no CPU path)")
+                   help="sm_100 CUDA device, e.g. cuda or cuda:1 (default cuda; there is no CPU path)")
     m.add_argument("-i", "--iou-thresh", type=float, default=0.3, metavar="<iou>",
-                   help="Non-maximum suppression IOU threshold. [Default 0.3]")
+                   help="boxes overlapping a kept box of their class by more than this IoU are dropped (default 0.3)")
     m.add_argument("-n", "--class-names", type=pathlib.Path, metavar="<path>",
-                   help="Path to text file of class names. If omitted, class index is displayed instead of name.")
+                   help="text file with one class name per line; without it boxes are labelled by class index")
     m.add_argument("-p", "--prob-thresh", type=float, default=0.05, metavar="<prob>",
-                   help="Detection probability threshold. [Default 0.05]")
+                   help="keep detections whose class probability is at least this (default 0.05)")
     m.add_argument("-w", "--weights", type=pathlib.Path, required=True, metavar="<path>",
-                   help="[Required] Path to Darknet model weights file.")
-    o = p.add_argument_group(title="Output/display options")
+                   help="Darknet .weights file for that network (required)")
+    o = p.add_argument_group(title="display and output")
     o.add_argument("-o", "--output", type=pathlib.Path, metavar="<path>",
-                   help="Path for writing output video file (.mp4).")
-    o.add_argument("--show-fps", action="store_true", help="Display frames processed per second (for --cam input).")
-    o.add_argument("-v", "--verbose", action="store_true", help="Verbose output")
+                   help="write the annotated frames to this .mp4")
+    o.add_argument("--show-fps", action="store_true", help="overlay the processing rate on the webcam view")
+    o.add_argument("-v", "--verbose", action="store_true", help="print the device name and timing")
     b = p.add_argument_group(title="batching (this implementation)")
     b.add_argument("-b", "--batch-size", type=int, default=16, metavar="<n>",
                    help="Images / frames per GPU batch in --image and --video modes. [Default 16]")
