@@ -390,8 +390,8 @@ class _Stager(threading.Thread):
         q = self.free.get((B, H, W))
         if q is None:
             q = self.free[(B, H, W)] = queue.Queue()
-            for _ in range(self.ring):
-                q.put((_pinned((B, H, W, 3), torch.uint8), _pinned((B, 2), torch.int32)))
+            for _ in range(self.ring):  # [staging image buffer (allocated on first use), original sizes]
+                q.put([None, _pinned((B, 2), torch.int32)])
         return q
 
     def run(self):
@@ -406,15 +406,16 @@ class _Stager(threading.Thread):
                 if self.stop:
                     break
                 t1 = time.perf_counter()
-                direct = _pinned_view(images, H, W)
-                if direct is not None:
-                    bufs = (bufs[0], bufs[1], direct)  # upload from the caller's page-locked images
-                else:
+                src = _pinned_view(images, H, W)  # upload straight from the caller's page-locked images ...
+                if src is None:                   # ... or stack them into this entry's pinned staging buffer
+                    if bufs[0] is None:
+                        bufs[0] = _pinned((B, H, W, 3), torch.uint8)
                     _stack_into(bufs[0].numpy(), images)
+                    src = bufs[0]
                 bufs[1].numpy()[...] = np.asarray([[s[0], s[1]] for s in orig_shapes], dtype=np.int32)
                 if self.stats is not None:
                     self.stats["stage"] = self.stats.get("stage", 0.0) + time.perf_counter() - t1
-                self.out.put(("batch", (B, H, W), bufs, q))
+                self.out.put(("batch", (B, H, W), (src, bufs), q))
             self.out.put(("end", None, None, None))
         except BaseException as e:  # noqa: BLE001 - re-raised in the consumer thread
             self.out.put(("error", e, None, None))
@@ -482,8 +483,8 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
                 yield_ready.append(finish(pending.popleft()))
             eng = slot.eng
             with torch.cuda.stream(slot.stream):
-                eng.in_u8.copy_(bufs[2] if len(bufs) == 3 else bufs[0], non_blocking=True)
-                eng.orig_hw.copy_(bufs[1], non_blocking=True)
+                eng.in_u8.copy_(bufs[0], non_blocking=True)       # bufs = (upload source, ring entry)
+                eng.orig_hw.copy_(bufs[1][1], non_blocking=True)
                 eng.launch((program,) + thr)
                 slot.meta.copy_(eng.meta, non_blocking=True)
                 if gather is not None:
@@ -500,7 +501,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
         slot.ev_meta.synchronize()
         t1 = time.perf_counter()
         tick("wait_gpu", t1 - t0)
-        it["free_q"].put(it["bufs"][:2])  # its upload is long done: the stager may refill the pinned buffers
+        it["free_q"].put(it["bufs"][1])  # its upload is long done: the stager may refill the ring entry
         per_image, total, class_kept, first_box = _split_meta(slot.meta.numpy(), B, eng.num_classes)
         it["per_image"] = per_image.copy()
         it["total"] = total
@@ -564,7 +565,7 @@ def inference_batches(net, batches, device="cuda", prob_thresh=0.05, nms_iou_thr
     finally:
         stager.stop = True
         for q in list(stager.free.values()):  # wake a stager that waits for a buffer (generator closed early)
-            q.put((None, None))
+            q.put([None, None])
         try:
             while True:  # ... or for room in the hand-over queue
                 stager.out.get_nowait()
